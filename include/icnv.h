@@ -1,0 +1,144 @@
+/*
+ * libicnv — B200 (sm_100a) CNV-inference hot path behind a plain C ABI.
+ *
+ * The reference (icbi-lab/infercnvpy @ 89aac1e) is pure Python and has no FFI of
+ * its own; these entry points are what a ctypes binding inside
+ * src/infercnvpy/tl/_infercnv.py would call in place of the numpy code cited on
+ * each function (file:line into /root/reference/src/infercnvpy/).  See
+ * INTEGRATION.md for the binding stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ICNV_E* code otherwise;
+ *     icnv_last_error() returns a thread-local human-readable message;
+ *   - all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - nothing here knows about torch, AnnData or NCCL: cross-GPU reduction of
+ *     the column sums is done by the caller between icnv_colsum_* and
+ *     icnv_plan_set_reference (one all-reduce).
+ */
+#ifndef ICNV_H
+#define ICNV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICNV_OK 0
+#define ICNV_EINVAL (-1)      /* bad argument */
+#define ICNV_ECUDA (-2)       /* CUDA runtime error */
+#define ICNV_EUNSUPPORTED (-3) /* shape outside what the kernels cover (message says why) */
+
+typedef struct icnv_plan icnv_plan;
+
+const char* icnv_last_error(void);
+int icnv_version(void);
+
+/* ------------------------------------------------------------------ plan ----
+ * Gene-axis plan = everything that depends on var/window/step but not on the
+ * cells: position-sorted gene order per chromosome, window grid, output
+ * offsets.  Replaces the per-chunk pandas work of
+ * tl/_infercnv.py:327-351 (_running_mean_by_chromosome /
+ * _running_mean_for_chromosome) and the window bookkeeping of :205-218.
+ *
+ *   n_genes    columns of the expression matrix (before any masking)
+ *   n_seg      chromosomes that take part, in output order (natural sort)
+ *   gene_idx_host[seg_off_host[n_seg]]  original column of the p-th gene in
+ *              position order, segments concatenated (integer permutation
+ *              computed by the host with the reference's own pandas call so
+ *              tie order matches)
+ *   seg_off_host[n_seg+1]
+ *   window, step   tl/_infercnv.py:25-26
+ */
+int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* gene_idx_host,
+                     const int32_t* seg_off_host, int32_t window, int32_t step, icnv_plan** out);
+void icnv_plan_destroy(icnv_plan* plan);
+
+/* Output width K and per-segment first output column (== chr_pos values of
+ * tl/_infercnv.py:335-337).  out_off_host has n_seg+1 entries. */
+int icnv_plan_out_width(const icnv_plan* plan, int64_t* K);
+int icnv_plan_out_offsets(const icnv_plan* plan, int64_t* out_off_host);
+/* 0 = templated group kernel, 1 = runtime group kernel, 2 = direct-form kernel */
+int icnv_plan_kernel_tier(const icnv_plan* plan);
+
+/* ------------------------------------------------------- reference profile --
+ * Column sums for the reference profile: tl/_infercnv.py:385 (all cells) and
+ * :400 (one mean per category).  Accumulates in float64.
+ *   row_cat   [n_rows] category of each row, -1 = not a reference cell;
+ *             NULL = every row belongs to category 0
+ *   sums      [n_cat, G] float64, OVERWRITTEN with this shard's sums
+ *   counts    [n_cat] int64, OVERWRITTEN with this shard's row counts
+ */
+int icnv_colsum_dense_f32(const float* X, int64_t n_rows, int64_t ldx, int32_t G, const int32_t* row_cat,
+                          int32_t n_cat, double* sums, int64_t* counts, void* stream);
+int icnv_colsum_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                        int32_t G, const int32_t* row_cat, int32_t n_cat, double* sums, int64_t* counts,
+                        void* stream);
+/* mean = sums / counts; written as float32 (the dtype numpy gives for a float32
+ * matrix) or, with out_is_f64 != 0, as float64 (integer / float64 matrices). */
+int icnv_mean_from_sums(const double* sums, const int64_t* counts, int32_t n_cat, int32_t G, void* ref_out,
+                        int32_t out_is_f64, void* stream);
+/* indptr[0] = 0, indptr[i+1] = sum(row_nnz[0..i]) (int64); n_rows + 1 entries. */
+int icnv_nnz_to_indptr(const int32_t* row_nnz, int64_t n_rows, int64_t* indptr, void* stream);
+
+/* Install the reference profile [n_cat, n_genes] (row-major, device) into the
+ * plan: builds the position-sorted per-gene bounds used for centring,
+ * tl/_infercnv.py:422-432 (n_cat == 1: x - ref; n_cat > 1: bounded difference
+ * against min/max over categories).  ref_is_f64 != 0 selects float64 centring
+ * (numpy promotes float32 - float64). */
+int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int32_t ref_is_f64, void* stream);
+
+/* ------------------------------------------------------------- smoothing ----
+ * Steps 1-4 of tl/_infercnv.py:411-442 for n_rows cells: centre, clip to
+ * +-lfc_clip, per-chromosome pyramid running mean decimated by `step`
+ * (:179-244, :301-356), subtract the row median.
+ *   out        [n_rows, ldo] float32 (out_is_f64 == 0) or float64
+ *   row_stats  [n_rows, 2] float64: sum and sum of squares of the row of `out`
+ *              (inputs of the per-chunk std of :450)
+ */
+int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip,
+                          void* out, int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream);
+int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* indices, const float* data,
+                        int64_t n_rows, double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo,
+                        double* row_stats, void* stream);
+
+/* Step 5, tl/_infercnv.py:449-451.  Rows are cut into consecutive chunks of
+ * chunk_rows (the reference's `chunksize`, :123); thr[c] = dyn_thr *
+ * population-std over every element of chunk c.  thr has ceil(n_rows /
+ * chunk_rows) entries. */
+int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int64_t chunk_rows, double dyn_thr,
+                         double* thr, void* stream);
+/* Zero |v| < thr[chunk of row] in place; also emits per row sum|v| and the
+ * number of non-zeros (inputs of cnv_score, tl/_scores.py:66, and of the CSR
+ * conversion, tl/_infercnv.py:455).  thr == NULL: no zeroing, statistics only. */
+int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                         const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream);
+
+/* Dense [n_rows, K] -> CSR (tl/_infercnv.py:455).  indptr [n_rows+1] int64 must
+ * already hold the exclusive prefix sum of row_nnz; indices int32; data float32
+ * or float64 following out_is_f64. */
+int icnv_dense_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo,
+                      const int64_t* indptr, int32_t* indices, void* data, void* stream);
+
+/* ------------------------------------------------------------- cnv_score ----
+ * tl/_scores.py:65-68: per label mean(abs(X_cnv[rows of label, :])).
+ *   row_abs_sum [n_rows] float64;  labels [n_rows] int32 in [0, n_labels)
+ *   label_sum   [n_labels] float64, label_rows [n_labels] int64 (OVERWRITTEN;
+ *   all-reduce both across shards, then score = label_sum / (label_rows * K)). */
+int icnv_rowabs_csr(const int64_t* indptr, const void* data, int32_t data_is_f64, int64_t n_rows,
+                    double* row_abs_sum, void* stream);
+int icnv_rowabs_dense(const void* X, int32_t is_f64, int64_t n_rows, int64_t K, int64_t ld, double* row_abs_sum,
+                      void* stream);
+int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_rows, int32_t n_labels,
+                    double* label_sum, int64_t* label_rows, void* stream);
+
+/* Launch geometry of the smoothing kernel chosen for this plan (for the bench
+ * and the ncu notes): CTAs per SM, threads, dynamic shared memory bytes. */
+int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* threads, int32_t* smem_bytes,
+                          int32_t* n_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICNV_H */

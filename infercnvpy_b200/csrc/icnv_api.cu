@@ -1,0 +1,544 @@
+// C ABI of libicnv (include/icnv.h) and the gene-axis plan.
+#include <algorithm>
+#include <memory>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/icnv.h"
+#include "icnv_common.cuh"
+
+namespace icnv {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+    return ICNV_ECUDA;
+}
+
+// aux launchers (icnv_aux.cu)
+int aux_colsum_dense(const float*, int64_t, int64_t, int, const int32_t*, int, double*, int64_t*, double*, int, cudaStream_t);
+int aux_colsum_csr(const int64_t*, const int32_t*, const float*, int64_t, int, const int32_t*, int, double*, int64_t*, cudaStream_t);
+int aux_mean_from_sums(const double*, const int64_t*, int, int, void*, bool, cudaStream_t);
+int aux_nnz_to_indptr(const int32_t*, int64_t, int64_t*, cudaStream_t);
+int aux_build_bounds(const void*, bool, int, int, const int32_t*, int64_t, void*, void*, bool, cudaStream_t);
+int aux_chunk_threshold(const double*, int64_t, int64_t, int64_t, double, double*, cudaStream_t);
+int aux_apply_threshold(void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
+int aux_dense_to_csr(const void*, bool, int64_t, int64_t, int64_t, const int64_t*, int32_t*, void*, cudaStream_t);
+int aux_rowabs_csr(const int64_t*, const void*, bool, int64_t, double*, cudaStream_t);
+int aux_rowabs_dense(const void*, bool, int64_t, int64_t, int64_t, double*, cudaStream_t);
+int aux_label_sums(const double*, const int32_t*, int64_t, int, double*, int64_t*, cudaStream_t);
+size_t smooth_scratch_bytes();
+
+template <typename T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t n = 0;
+    int upload(const std::vector<T>& h) {
+        n = h.size();
+        if (n == 0) return 0;
+        ICNV_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+        ICNV_CUDA(cudaMemcpy(ptr, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int alloc(size_t count) {
+        n = count;
+        if (n == 0) return 0;
+        ICNV_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+        return 0;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace icnv
+
+using namespace icnv;
+
+struct icnv_plan {
+    int device = 0;
+    int n_sm = 148;
+    int32_t G = 0, n_seg = 0, window = 0, step = 0;
+    std::vector<int32_t> seg_off, gene_idx;
+    std::vector<int64_t> out_off;  // n_seg + 1
+    int64_t K = 0;
+    double inv_sumw = 1.0;
+
+    // ---- grouped layout (tiers 0/1); valid when group_ok
+    bool group_ok = false;
+    int base_tier = 2;
+    int32_t gs = 0, NG = 0, NGpad = 0, NQ = 0, qstar = -1, Gpad = 0;
+    int32_t n_tasks_g = 0;
+    DevBuf<uint16_t> idx_t;
+    DevBuf<int32_t> cols_t;  // same layout as idx_t, int32, pad = -1 (input of the bounds kernel)
+    DevBuf<float> lo_t, hi_t;
+    DevBuf<double> alpha, beta, cw;
+    DevBuf<Task> tasks_g;
+
+    // ---- direct layout (tier 2); always built
+    int32_t n_sorted = 0, n_tasks_d = 0;
+    DevBuf<int32_t> idx_lin;
+    DevBuf<unsigned char> lo_lin, hi_lin;  // float or double
+    DevBuf<double> wdir;
+    DevBuf<Task> tasks_d;
+
+    DevBuf<double> flat_inv;
+
+    // ---- reference state
+    bool have_ref = false, bounded = false, c64 = false;
+
+    // ---- workspace for column sums
+    DevBuf<double> colsum_partial;
+
+    ~icnv_plan() {
+        idx_t.release();
+        cols_t.release();
+        lo_t.release();
+        hi_t.release();
+        alpha.release();
+        beta.release();
+        cw.release();
+        tasks_g.release();
+        idx_lin.release();
+        lo_lin.release();
+        hi_lin.release();
+        wdir.release();
+        tasks_d.release();
+        flat_inv.release();
+        colsum_partial.release();
+    }
+};
+
+namespace {
+
+constexpr size_t SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+size_t smem_grouped(const icnv_plan& p, int tier) {
+    size_t s = smooth_scratch_bytes();
+    s += (size_t)p.Gpad * 4;
+    s += (size_t)(p.NGpad + PAD_GROUPS) * 16;
+    if (p.qstar >= 0) s += (size_t)(p.NGpad + PAD_GROUPS) * 8;
+    if (tier == 1) s += (size_t)p.NQ * 16 + (size_t)p.gs * 8;
+    return (s + 15) / 16 * 16;
+}
+size_t smem_direct(const icnv_plan& p, bool c64) {
+    size_t s = smooth_scratch_bytes();
+    s += (size_t)p.window * 8;
+    s += (size_t)(p.n_sorted + 4) * (c64 ? 8 : 4);
+    return (s + 15) / 16 * 16;
+}
+
+struct Choice {
+    int tier, nwin, gs, tpt;
+    size_t smem;
+};
+
+// which kernel instantiation runs for this plan + reference dtype
+int choose(const icnv_plan& p, bool c64, Choice* c) {
+    if (p.group_ok && !c64) {
+        const bool templ = (p.step == 10 && (p.window == 100 || p.window == 250));
+        if (templ && p.n_tasks_g <= NT && smem_grouped(p, 0) <= SMEM_MAX) {
+            *c = {0, p.window, p.gs, 1, smem_grouped(p, 0)};
+            return 0;
+        }
+        if (smem_grouped(p, 1) <= SMEM_MAX && p.n_tasks_g <= 4 * NT) {
+            *c = {1, 0, 0, p.n_tasks_g <= NT ? 1 : 4, smem_grouped(p, 1)};
+            return 0;
+        }
+    }
+    if (smem_direct(p, c64) > SMEM_MAX) {
+        set_error("gene axis too long for the shared-memory resident row of the direct kernel (" +
+                  std::to_string(p.n_sorted) + " genes" + (c64 ? ", float64 centring)" : ")"));
+        return ICNV_EUNSUPPORTED;
+    }
+    if (p.n_tasks_d > 8 * NT) {
+        set_error("output too wide for the register-resident median: K = " + std::to_string(p.K) + " > " +
+                  std::to_string(8 * NT * LOUT));
+        return ICNV_EUNSUPPORTED;
+    }
+    *c = {2, 0, 0, p.n_tasks_d <= NT ? 1 : 8, smem_direct(p, c64)};
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* icnv_last_error(void) { return g_err.c_str(); }
+int icnv_version(void) { return 100; }
+
+int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* gene_idx_host,
+                     const int32_t* seg_off_host, int32_t window, int32_t step, icnv_plan** out) {
+    if (!out || n_genes <= 0 || n_seg < 0 || window < 1 || step < 1 || (n_seg > 0 && (!gene_idx_host || !seg_off_host))) {
+        set_error("icnv_plan_create: bad argument");
+        return ICNV_EINVAL;
+    }
+    ICNV_CUDA(cudaSetDevice(device));
+    std::unique_ptr<icnv_plan> p(new icnv_plan());
+    p->device = device;
+    ICNV_CUDA(cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, device));
+    p->G = n_genes;
+    p->n_seg = n_seg;
+    p->window = window;
+    p->step = step;
+    p->seg_off.assign(seg_off_host, seg_off_host + n_seg + 1);
+    if (n_seg > 0 && p->seg_off[0] != 0) {
+        set_error("icnv_plan_create: seg_off[0] must be 0");
+        return ICNV_EINVAL;
+    }
+    const int32_t n_sorted = n_seg > 0 ? p->seg_off[n_seg] : 0;
+    p->gene_idx.assign(gene_idx_host, gene_idx_host + n_sorted);
+    for (int32_t i = 0; i < n_sorted; ++i)
+        if (p->gene_idx[i] < 0 || p->gene_idx[i] >= n_genes) {
+            set_error("icnv_plan_create: gene_idx out of range");
+            return ICNV_EINVAL;
+        }
+    p->n_sorted = n_sorted;
+
+    // ---- window grid per segment (tl/_infercnv.py:205-218, :227-236, :335-337)
+    const int n = window, s = step;
+    std::vector<int64_t> n_out(n_seg);
+    std::vector<char> is_flat(n_seg);
+    p->out_off.assign(n_seg + 1, 0);
+    for (int c = 0; c < n_seg; ++c) {
+        const int64_t Gc = p->seg_off[c + 1] - p->seg_off[c];
+        if (Gc <= 0) {
+            set_error("icnv_plan_create: empty segment");
+            return ICNV_EINVAL;
+        }
+        is_flat[c] = !(n < Gc);
+        n_out[c] = is_flat[c] ? 1 : (Gc - n) / s + 1;
+        p->out_off[c + 1] = p->out_off[c] + n_out[c];
+    }
+    p->K = p->out_off[n_seg];
+    {
+        long long sw = 0;
+        for (int j = 0; j < n; ++j) sw += pyr(n, j);
+        p->inv_sumw = 1.0 / (double)sw;
+    }
+
+    std::vector<double> flat_inv;
+    // ---- direct layout
+    {
+        std::vector<Task> tasks;
+        for (int c = 0; c < n_seg; ++c) {
+            const int32_t s0 = p->seg_off[c];
+            const int32_t Gc = p->seg_off[c + 1] - s0;
+            if (is_flat[c]) {
+                tasks.push_back({s0, (int32_t)p->out_off[c], Gc, 1 | ((int32_t)flat_inv.size() << 8)});
+                flat_inv.push_back(1.0 / (double)Gc);
+            } else {
+                for (int64_t t = 0; t * LOUT < n_out[c]; ++t)
+                    tasks.push_back({(int32_t)(s0 + t * LOUT * s), (int32_t)(p->out_off[c] + t * LOUT),
+                                     (int32_t)std::min<int64_t>(LOUT, n_out[c] - t * LOUT), 0});
+            }
+        }
+        p->n_tasks_d = (int32_t)tasks.size();
+        std::vector<double> w(n);
+        for (int j = 0; j < n; ++j) w[j] = (double)pyr(n, j);
+        if (p->idx_lin.upload(p->gene_idx) || p->tasks_d.upload(tasks) || p->wdir.upload(w)) return ICNV_ECUDA;
+    }
+
+    // ---- grouped layout: groups of gs = step genes when step | window
+    p->group_ok = (n % s == 0) && (n_genes < 65535);
+    if (p->group_ok) {
+        const int gs = s;
+        p->gs = gs;
+        p->NQ = n / gs;
+        std::vector<int32_t> gbase(n_seg + 1, 0);
+        for (int c = 0; c < n_seg; ++c) {
+            const int64_t Gc = p->seg_off[c + 1] - p->seg_off[c];
+            const int64_t ng = is_flat[c] ? (Gc + gs - 1) / gs : ((n_out[c] - 1) * s + n) / gs;
+            gbase[c + 1] = gbase[c] + (int32_t)ng;
+        }
+        p->NG = gbase[n_seg];
+        p->NGpad = (p->NG + 3) / 4 * 4;
+        if (p->NGpad == 0) p->NGpad = 4;
+        p->Gpad = (n_genes + 1 + 3) / 4 * 4;
+        std::vector<uint16_t> idx((size_t)gs * p->NGpad, (uint16_t)n_genes);
+        std::vector<int32_t> cols((size_t)gs * p->NGpad, -1);
+        for (int c = 0; c < n_seg; ++c) {
+            const int32_t s0 = p->seg_off[c];
+            const int32_t Gc = p->seg_off[c + 1] - s0;
+            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g)
+                for (int j = 0; j < gs; ++j) {
+                    const int32_t pos = (g - gbase[c]) * gs + j;
+                    if (pos < Gc) {
+                        idx[(size_t)j * p->NGpad + g] = (uint16_t)p->gene_idx[s0 + pos];
+                        cols[(size_t)j * p->NGpad + g] = p->gene_idx[s0 + pos];
+                    }
+                }
+        }
+        // weights: within a group the pyramid is linear in j except (at most) the group holding the peak
+        std::vector<double> alpha(p->NQ, 0.0), beta(p->NQ, 0.0), cw(gs, 0.0);
+        p->qstar = -1;
+        for (int q = 0; q < p->NQ; ++q) {
+            const int a = pyr(n, gs * q);
+            const int b = gs > 1 ? pyr(n, gs * q + 1) - a : 0;
+            bool linear = true;
+            for (int j = 0; j < gs; ++j) linear = linear && (pyr(n, gs * q + j) == a + b * j);
+            if (linear) {
+                alpha[q] = a;
+                beta[q] = b;
+            } else {
+                if (p->qstar >= 0) {
+                    set_error("internal: two non-linear weight groups");
+                    return ICNV_EINVAL;
+                }
+                p->qstar = q;
+                for (int j = 0; j < gs; ++j) cw[j] = pyr(n, gs * q + j);
+            }
+        }
+        std::vector<Task> tasks;
+        for (int c = 0; c < n_seg; ++c) {
+            if (is_flat[c]) {
+                int fid = 0;  // same order as the direct layout
+                for (int cc = 0; cc < c; ++cc) fid += is_flat[cc];
+                tasks.push_back({gbase[c], (int32_t)p->out_off[c], gbase[c + 1] - gbase[c], 1 | (fid << 8)});
+            } else {
+                for (int64_t t = 0; t * LOUT < n_out[c]; ++t)
+                    tasks.push_back({(int32_t)(gbase[c] + t * LOUT), (int32_t)(p->out_off[c] + t * LOUT),
+                                     (int32_t)std::min<int64_t>(LOUT, n_out[c] - t * LOUT), 0});
+            }
+        }
+        p->n_tasks_g = (int32_t)tasks.size();
+        if (p->idx_t.upload(idx) || p->cols_t.upload(cols) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
+            p->cw.upload(cw) || p->tasks_g.upload(tasks))
+            return ICNV_ECUDA;
+        if (p->lo_t.alloc(idx.size()) || p->hi_t.alloc(idx.size())) return ICNV_ECUDA;
+    }
+    if (flat_inv.empty()) flat_inv.push_back(1.0);
+    if (p->flat_inv.upload(flat_inv)) return ICNV_ECUDA;
+    if (p->lo_lin.alloc((size_t)(n_sorted + 4) * 8) || p->hi_lin.alloc((size_t)(n_sorted + 4) * 8)) return ICNV_ECUDA;
+
+    Choice ch;
+    p->base_tier = choose(*p, false, &ch) == 0 ? ch.tier : -1;
+    *out = p.release();
+    return ICNV_OK;
+}
+
+void icnv_plan_destroy(icnv_plan* plan) { delete plan; }
+
+int icnv_plan_out_width(const icnv_plan* plan, int64_t* K) {
+    if (!plan || !K) return ICNV_EINVAL;
+    *K = plan->K;
+    return ICNV_OK;
+}
+int icnv_plan_out_offsets(const icnv_plan* plan, int64_t* out_off_host) {
+    if (!plan || !out_off_host) return ICNV_EINVAL;
+    std::copy(plan->out_off.begin(), plan->out_off.end(), out_off_host);
+    return ICNV_OK;
+}
+int icnv_plan_kernel_tier(const icnv_plan* plan) {
+    if (!plan) return ICNV_EINVAL;
+    Choice ch;
+    if (choose(*plan, plan->c64, &ch)) return ICNV_EUNSUPPORTED;
+    return ch.tier;
+}
+
+int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* threads, int32_t* smem_bytes, int32_t* n_sm) {
+    if (!plan) return ICNV_EINVAL;
+    Choice ch;
+    int rc = choose(*plan, plan->c64, &ch);
+    if (rc) return rc;
+    int occ = 0;
+    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.smem, &occ);
+    if (rc) return rc;
+    if (ctas_per_sm) *ctas_per_sm = occ;
+    if (threads) *threads = NT;
+    if (smem_bytes) *smem_bytes = (int32_t)ch.smem;
+    if (n_sm) *n_sm = plan->n_sm;
+    return ICNV_OK;
+}
+
+int icnv_colsum_dense_f32(const float* X, int64_t n_rows, int64_t ldx, int32_t G, const int32_t* row_cat, int32_t n_cat,
+                          double* sums, int64_t* counts, void* stream) {
+    if (!X || !sums || !counts || n_rows < 0 || G <= 0 || n_cat <= 0 || ldx < G) {
+        set_error("icnv_colsum_dense_f32: bad argument");
+        return ICNV_EINVAL;
+    }
+    // row splits: enough CTAs to fill the machine, each with a decent run of rows
+    int n_split = (int)std::min<int64_t>(std::max<int64_t>(1, n_rows / 64), 4 * 148 / std::max(1, (G + 1023) / 1024) + 1);
+    double* partial = nullptr;
+    ICNV_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)n_split * n_cat * G, (cudaStream_t)stream));
+    int rc = aux_colsum_dense(X, n_rows, ldx, G, row_cat, n_cat, sums, counts, partial, n_split, (cudaStream_t)stream);
+    cudaFreeAsync(partial, (cudaStream_t)stream);
+    return rc;
+}
+
+int icnv_colsum_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows, int32_t G,
+                        const int32_t* row_cat, int32_t n_cat, double* sums, int64_t* counts, void* stream) {
+    if (!indptr || !sums || !counts || n_rows < 0 || G <= 0 || n_cat <= 0) {
+        set_error("icnv_colsum_csr_f32: bad argument");
+        return ICNV_EINVAL;
+    }
+    return aux_colsum_csr(indptr, indices, data, n_rows, G, row_cat, n_cat, sums, counts, (cudaStream_t)stream);
+}
+
+int icnv_mean_from_sums(const double* sums, const int64_t* counts, int32_t n_cat, int32_t G, void* ref_out, int32_t out_is_f64,
+                        void* stream) {
+    if (!sums || !counts || !ref_out) return ICNV_EINVAL;
+    return aux_mean_from_sums(sums, counts, n_cat, G, ref_out, out_is_f64 != 0, (cudaStream_t)stream);
+}
+int icnv_nnz_to_indptr(const int32_t* row_nnz, int64_t n_rows, int64_t* indptr, void* stream) {
+    if (!indptr || n_rows < 0 || (n_rows > 0 && !row_nnz)) return ICNV_EINVAL;
+    return aux_nnz_to_indptr(row_nnz, n_rows, indptr, (cudaStream_t)stream);
+}
+
+int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int32_t ref_is_f64, void* stream) {
+    if (!plan || !ref || n_cat < 1) {
+        set_error("icnv_plan_set_reference: bad argument");
+        return ICNV_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool c64 = ref_is_f64 != 0;
+    Choice ch;
+    int rc = choose(*plan, c64, &ch);
+    if (rc) return rc;
+    if (ch.tier < 2) {
+        rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->cols_t.ptr, (int64_t)plan->cols_t.n, plan->lo_t.ptr,
+                              plan->hi_t.ptr, false, st);
+    } else {
+        rc = aux_build_bounds(ref, c64, n_cat, plan->G, plan->idx_lin.ptr, plan->n_sorted, plan->lo_lin.ptr,
+                              plan->hi_lin.ptr, c64, st);
+    }
+    if (rc) return rc;
+    plan->have_ref = true;
+    plan->bounded = n_cat > 1;
+    plan->c64 = c64;
+    return ICNV_OK;
+}
+
+static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo,
+                         double* row_stats, void* stream) {
+    if (!plan->have_ref) {
+        set_error("smooth: icnv_plan_set_reference has not been called");
+        return ICNV_EINVAL;
+    }
+    if (!out || !row_stats || ldo < plan->K || !(lfc_clip >= 0)) {
+        set_error("smooth: bad argument");
+        return ICNV_EINVAL;
+    }
+    if (sp.n_rows == 0 || plan->K == 0) return ICNV_OK;
+    Choice ch;
+    int rc = choose(*plan, plan->c64, &ch);
+    if (rc) return rc;
+    if (ch.tier == 2 && !sp.X) {
+        set_error("smooth: CSR input is only fused into the grouped kernels; densify first for this (window, step)");
+        return ICNV_EUNSUPPORTED;
+    }
+    sp.G = plan->G;
+    sp.Gpad = plan->Gpad;
+    sp.gs = plan->gs;
+    sp.NG = plan->NG;
+    sp.NGpad = plan->NGpad;
+    sp.NQ = plan->NQ;
+    sp.qstar = plan->qstar;
+    sp.idx_t = plan->idx_t.ptr;
+    sp.lo_t = plan->lo_t.ptr;
+    sp.hi_t = plan->hi_t.ptr;
+    sp.alpha = plan->alpha.ptr;
+    sp.beta = plan->beta.ptr;
+    sp.cw = plan->cw.ptr;
+    sp.window = plan->window;
+    sp.step = plan->step;
+    sp.n_sorted = plan->n_sorted;
+    sp.idx_lin = plan->idx_lin.ptr;
+    sp.lo_lin = plan->lo_lin.ptr;
+    sp.hi_lin = plan->hi_lin.ptr;
+    sp.wdir = plan->wdir.ptr;
+    sp.clip = plan->c64 ? lfc_clip : (double)(float)lfc_clip;
+    sp.inv_sumw = plan->inv_sumw;
+    sp.flat_inv = plan->flat_inv.ptr;
+    sp.tasks = ch.tier < 2 ? plan->tasks_g.ptr : plan->tasks_d.ptr;
+    sp.n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+    sp.K = (int32_t)plan->K;
+    sp.out = out;
+    sp.ldo = ldo;
+    sp.out_f64 = out_is_f64;
+    sp.row_stats = row_stats;
+    sp.use_tma = sp.X && (sp.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp.X) & 15) == 0) && (plan->G % 4 == 0);
+    int occ = 0;
+    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.smem, &occ);
+    if (rc) return rc;
+    if (occ < 1) {
+        set_error("smooth: kernel does not fit on an SM");
+        return ICNV_EUNSUPPORTED;
+    }
+    const int grid = (int)std::min<int64_t>(sp.n_rows, (int64_t)plan->n_sm * occ);
+    return smooth_launch(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, sp, grid, ch.smem, (cudaStream_t)stream);
+}
+
+int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip, void* out,
+                          int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream) {
+    if (!plan || !X || n_rows < 0 || ldx < plan->G) {
+        set_error("icnv_smooth_dense_f32: bad argument");
+        return ICNV_EINVAL;
+    }
+    SmoothParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.X = X;
+    sp.ldx = ldx;
+    sp.n_rows = n_rows;
+    return smooth_common(plan, sp, lfc_clip, out, out_is_f64, ldo, row_stats, stream);
+}
+
+int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                        double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream) {
+    if (!plan || !indptr || n_rows < 0) {
+        set_error("icnv_smooth_csr_f32: bad argument");
+        return ICNV_EINVAL;
+    }
+    SmoothParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.indptr = indptr;
+    sp.indices = indices;
+    sp.data = data;
+    sp.n_rows = n_rows;
+    return smooth_common(plan, sp, lfc_clip, out, out_is_f64, ldo, row_stats, stream);
+}
+
+int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int64_t chunk_rows, double dyn_thr, double* thr,
+                         void* stream) {
+    if (!row_stats || !thr || chunk_rows < 1 || K < 1) {
+        set_error("icnv_chunk_threshold: bad argument");
+        return ICNV_EINVAL;
+    }
+    return aux_chunk_threshold(row_stats, n_rows, K, chunk_rows, dyn_thr, thr, (cudaStream_t)stream);
+}
+
+int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                         const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream) {
+    if (!out || chunk_rows < 1 || ldo < K) {
+        set_error("icnv_apply_threshold: bad argument");
+        return ICNV_EINVAL;
+    }
+    return aux_apply_threshold(out, out_is_f64 != 0, n_rows, K, ldo, chunk_rows, thr, row_abs_sum, row_nnz, (cudaStream_t)stream);
+}
+
+int icnv_dense_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, const int64_t* indptr,
+                      int32_t* indices, void* data, void* stream) {
+    if (!out || !indptr) return ICNV_EINVAL;
+    return aux_dense_to_csr(out, out_is_f64 != 0, n_rows, K, ldo, indptr, indices, data, (cudaStream_t)stream);
+}
+
+int icnv_rowabs_csr(const int64_t* indptr, const void* data, int32_t data_is_f64, int64_t n_rows, double* row_abs_sum,
+                    void* stream) {
+    if (!indptr || !row_abs_sum) return ICNV_EINVAL;
+    return aux_rowabs_csr(indptr, data, data_is_f64 != 0, n_rows, row_abs_sum, (cudaStream_t)stream);
+}
+int icnv_rowabs_dense(const void* X, int32_t is_f64, int64_t n_rows, int64_t K, int64_t ld, double* row_abs_sum, void* stream) {
+    if (!X || !row_abs_sum) return ICNV_EINVAL;
+    return aux_rowabs_dense(X, is_f64 != 0, n_rows, K, ld, row_abs_sum, (cudaStream_t)stream);
+}
+int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_rows, int32_t n_labels, double* label_sum,
+                    int64_t* label_rows, void* stream) {
+    if (!row_abs_sum || !labels || !label_sum || !label_rows) return ICNV_EINVAL;
+    return aux_label_sums(row_abs_sum, labels, n_rows, n_labels, label_sum, label_rows, (cudaStream_t)stream);
+}
+
+}  // extern "C"

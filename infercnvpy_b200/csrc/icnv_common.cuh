@@ -1,0 +1,143 @@
+// Shared declarations for libicnv (sm_100a).  See include/icnv.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace icnv {
+
+constexpr int NT = 512;         // threads per CTA of the smoothing kernel
+constexpr int NW = NT / 32;     // warps per CTA
+constexpr int LOUT = 5;         // consecutive outputs owned by one task (odd -> conflict-free smem strides)
+constexpr int CAND_CAP = 32;    // median: size of the final exact candidate set
+constexpr int PAD_GROUPS = 8;   // slack groups after the last one (sliding window over-read)
+
+// pyramid weight j of an n-wide window: min(j + 1, n - j)  (tl/_infercnv.py:206-207)
+__host__ __device__ constexpr int pyr(int n, int j) { return (j + 1) < (n - j) ? (j + 1) : (n - j); }
+
+// One task = up to LOUT consecutive outputs of one chromosome (kind 0), or the single
+// flat-mean output of a chromosome not longer than the window (kind 1).
+//   kind 0: x = first group (tiers 0/1) or first sorted gene (tier 2); y = first output column;
+//           z = number of outputs (1..LOUT)
+//   kind 1: x as above; y = output column; z = number of groups (tiers 0/1) or genes (tier 2);
+//           w >> 8 = index into flat_inv
+struct Task {
+    int32_t x, y, z, w;
+};
+
+struct SmoothParams {
+    // ---- input matrix: dense (X != null) or CSR
+    const float* X;
+    int64_t ldx;
+    const int64_t* indptr;
+    const int32_t* indices;
+    const float* data;
+    int64_t n_rows;
+    int32_t G;        // columns of X
+    int32_t Gpad;     // staged floats (>= G+1, multiple of 4); slot G is the zero pad
+    int32_t use_tma;  // row base and pitch 16-byte aligned -> cp.async.bulk
+    // ---- grouped tiers (0/1)
+    int32_t gs;       // genes per group (== step)
+    int32_t NG;       // groups
+    int32_t NGpad;    // multiple of 4
+    int32_t NQ;       // groups per window
+    int32_t qstar;    // group-in-window holding the pyramid peak (non-linear weights), -1 if none
+    const uint16_t* idx_t;  // [gs][NGpad] column of X for element j of group g (G = zero pad)
+    const float* lo_t;      // [gs][NGpad] reference lower bound (== ref when one category)
+    const float* hi_t;      // [gs][NGpad] upper bound (only read when BOUNDED)
+    const double* alpha;    // [NQ] weight of A_g = sum_j x
+    const double* beta;     // [NQ] weight of B_g = sum_j j*x
+    const double* cw;       // [gs] weights inside the peak group (C_g = sum_j cw_j x)
+    // ---- direct tier (2)
+    int32_t window;
+    int32_t step;
+    int32_t n_sorted;       // genes in position order, all segments
+    const int32_t* idx_lin; // [n_sorted]
+    const void* lo_lin;     // [n_sorted] float or double (C64)
+    const void* hi_lin;
+    const double* wdir;     // [window] pyramid weights
+    // ---- common
+    double clip;
+    double inv_sumw;
+    const double* flat_inv; // 1 / (genes of flat segment)
+    const Task* tasks;
+    int32_t n_tasks;
+    int32_t K;
+    void* out;
+    int64_t ldo;
+    int32_t out_f64;
+    double* row_stats;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_nc_u2(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define ICNV_CUDA(expr)                                          \
+    do {                                                         \
+        cudaError_t _e = (expr);                                 \
+        if (_e != cudaSuccess) return ::icnv::cuda_fail(_e, #expr); \
+    } while (0)
+
+// Launchers implemented in icnv_smooth.cu
+int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, const SmoothParams& p, int grid,
+                  size_t smem, cudaStream_t stream);
+int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, size_t smem, int* ctas_per_sm);
+
+}  // namespace icnv

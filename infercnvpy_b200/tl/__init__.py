@@ -1,0 +1,6 @@
+"""Tools: ``cnv.tl.*`` (reference: ``/root/reference/src/infercnvpy/tl/__init__.py``)."""
+
+from ._infercnv import infercnv
+from ._scores import cnv_score
+
+__all__ = ["infercnv", "cnv_score"]

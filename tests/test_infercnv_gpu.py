@@ -1,0 +1,252 @@
+"""Parity of the CUDA path (through the C ABI / public API) with the oracle and the goldens.
+
+Tolerances.  The kernels accumulate every window in float64 and round once to float32, so
+against the reference's float64 result the float32 output is within 1 ulp(float32) ~ 6e-8
+relative; ``north_star`` asks for 1e-5.  We assert 1e-6 relative on every entry both sides keep,
+and with float64 output 1e-11.  Entries the noise filter keeps on one side and zeroes on the other
+("flips") are only legal if the value sits within float32 rounding of the chunk threshold.
+"""
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+import infercnvpy_b200 as cnv
+from oracle import infercnv_oracle as orc
+from tests.golden.cases import CASES, build_case
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-6
+
+
+def _torch():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+def _adata(X, var, obs=None):
+    return cnv.AnnData(X, obs=obs, var=var)
+
+
+def _compare_thresholded(got: np.ndarray, want: np.ndarray, chunk: int, rtol=RTOL32, what=""):
+    """Both dense float64 [n, K].  Values both sides keep must agree to ``rtol``; an entry kept on one
+    side only ("flip") is legal only if it sits on the chunk's noise threshold, i.e. its magnitude is
+    within 1e-5 relative of the smallest magnitude the reference keeps in that chunk.  Returns #flips."""
+    assert got.shape == want.shape
+    both = (got != 0) & (want != 0)
+    np.testing.assert_allclose(got[both], want[both], rtol=rtol, atol=0, err_msg=what)
+    n_flips = 0
+    for r0 in range(0, got.shape[0], chunk):
+        g, w = got[r0 : r0 + chunk], want[r0 : r0 + chunk]
+        flips = (g != 0) != (w != 0)
+        if not flips.any():
+            continue
+        n_flips += int(flips.sum())
+        kept_min = np.abs(w[w != 0]).min() if (w != 0).any() else 0.0
+        val = np.where(g[flips] != 0, np.abs(g[flips]), np.abs(w[flips]))
+        assert np.all(val <= kept_min * (1 + 1e-5)), f"{what}: flip away from the threshold in chunk at row {r0}"
+    assert n_flips <= max(1, int(1e-6 * got.size)), f"{what}: {n_flips} flips"
+    return n_flips
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_public_api_matches_reference_golden(case, golden_loader):
+    """cnv.tl.infercnv with the reference's own profile == the real reference's output."""
+    gold = golden_loader(case["name"])
+    X, var, obs, kw = build_case(case)
+    kw = {k: v for k, v in kw.items() if k not in ("reference_key", "reference_cat", "reference")}
+    Xin = sp.csr_matrix(X) if case.get("container") == "csr" else X
+    adata = _adata(Xin, var, obs)
+    chr_pos, res, per_gene = cnv.tl.infercnv(adata, reference=gold["profile"], inplace=False, **kw)
+    assert per_gene is None
+    assert {k: int(v) for k, v in chr_pos.items()} == gold["chr_pos"]
+    assert list(chr_pos) == list(gold["chr_pos"])
+    assert sp.issparse(res) and res.dtype == np.float64 and res.shape == gold["csr"].shape
+    _compare_thresholded(res.toarray(), gold["csr"].toarray(), kw.get("chunksize", 5000), what=case["name"])
+
+
+@pytest.mark.parametrize("name", ["small_default", "small_cats", "small_onecat", "small_csr", "g20k_win100"])
+def test_data_derived_reference_profile(name, golden_loader):
+    """Reference profile computed on the device (all cells / per category, dense and CSR)."""
+    torch = _torch()
+    from infercnvpy_b200._engine import DevicePlan
+    from infercnvpy_b200._layout import build_layout
+    from infercnvpy_b200.tl._infercnv import _reference_categories, _rows_to_device
+
+    case = next(c for c in CASES if c["name"] == name)
+    gold = golden_loader(name)
+    X, var, obs, kw = build_case(case)
+    Xin = sp.csr_matrix(X) if case.get("container") == "csr" else X
+    adata = _adata(Xin, var, obs)
+    layout = build_layout(var, kw.get("window_size", 100), kw.get("step", 10))
+    dev = torch.device("cuda", 0)
+    with DevicePlan(layout, dev) as plan:
+        row_cat, n_cat = None, 1
+        if "reference_key" in kw:
+            rc, cats = _reference_categories(adata, kw["reference_key"], kw["reference_cat"])
+            row_cat, n_cat = torch.from_numpy(rc).to(dev), len(cats)
+        sums, counts = plan.colsum(_rows_to_device(Xin, 0, X.shape[0], dev), row_cat, n_cat)
+        ref = plan.mean_from_sums(sums, counts).cpu().numpy()
+    # numpy's float32 running mean vs our float64-accumulated mean: a few float32 ulps
+    np.testing.assert_allclose(ref, gold["profile"], rtol=2e-6, atol=1e-7)
+
+    # and the whole public path with the data-derived profile stays within 1e-5 absolute of the reference
+    kw2 = dict(kw)
+    chr_pos, res, _ = cnv.tl.infercnv(adata, inplace=False, **kw2)
+    got, want = res.toarray(), gold["csr"].toarray()
+    both = (got != 0) & (want != 0)
+    np.testing.assert_allclose(got[both], want[both], rtol=1e-4, atol=1e-6)
+    assert ((got != 0) != (want != 0)).mean() < 1e-3
+
+
+def test_float64_output_matches_oracle_to_1e11():
+    """C-ABI level: pre-threshold matrix with float64 output against the oracle (no noise filter)."""
+    torch = _torch()
+    from infercnvpy_b200._engine import DevicePlan
+    from infercnvpy_b200._layout import build_layout
+
+    dev = torch.device("cuda", 0)
+    for g, n_cells, window, step in [(20000, 64, 100, 10), (20000, 32, 250, 10), (6000, 40, 50, 10), (3000, 24, 20, 3)]:
+        var = cnv.datasets.synthetic_var(g, seed=3, with_extras=True)
+        X = cnv.datasets.synthetic_counts(n_cells, g, seed=g + window)
+        ref = X.mean(axis=0, dtype=np.float64).astype(np.float32)[None, :]
+        layout = build_layout(var, window, step)
+        with DevicePlan(layout, dev) as plan:
+            plan.set_reference(torch.from_numpy(ref).to(dev))
+            out, stats = plan.smooth(torch.from_numpy(X).to(dev), 3.0, out_dtype=torch.float64)
+            got = out.cpu().numpy()
+            stats = stats.cpu().numpy()
+            tier = plan.tier
+        chr_pos, want = orc.infercnv(
+            X, var["chromosome"].values, var["start"].values, reference=ref, window_size=window, step=step,
+            dynamic_threshold=None,
+        )
+        want = want.toarray()
+        assert {k: int(v) for k, v in chr_pos.items()} == {k: int(v) for k, v in layout.chr_pos.items()}
+        scale = np.abs(want).max()
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13 * scale, err_msg=f"tier {tier} window {window}")
+        np.testing.assert_allclose(stats[:, 0], want.sum(axis=1), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(stats[:, 1], (want**2).sum(axis=1), rtol=1e-10)
+
+
+def test_reference_known_answers(full_mock, x_res_actual):
+    """/root/reference/tests/test_tools.py:143-191 through the public API (integer matrix, CSR, 2 chunks)."""
+    X, var = full_mock
+    adata = _adata(sp.csr_matrix(X), var)
+    chr_pos, res, _ = cnv.tl.infercnv(
+        adata, chunksize=2, lfc_clip=1, window_size=3, step=1, dynamic_threshold=1, inplace=False
+    )
+    np.testing.assert_allclose(res.toarray(), x_res_actual, rtol=1e-6, atol=0)
+    assert chr_pos == {"chr1": 0, "chr2": 3}
+    # inplace keys (_infercnv.py:153-155)
+    cnv.tl.infercnv(adata, chunksize=2, lfc_clip=1, window_size=3, step=1, dynamic_threshold=1)
+    assert "X_cnv" in adata.obsm and adata.uns["cnv"]["chr_pos"] == {"chr1": 0, "chr2": 3}
+
+
+def test_errors_match_reference():
+    var = cnv.datasets.synthetic_var(300, seed=1)
+    X = cnv.datasets.synthetic_counts(8, 300, seed=1)
+    with pytest.raises(ValueError, match="Genomic positions not found"):
+        cnv.tl.infercnv(_adata(X, var.drop(columns=["start"])))
+    dup = var.copy()
+    dup.index = ["a"] * 300
+    with pytest.raises(ValueError, match="unique"):
+        cnv.tl.infercnv(_adata(X, dup))
+    with pytest.raises(ValueError, match="Reference must match"):
+        cnv.tl.infercnv(_adata(X, var), reference=np.ones(299))
+    obs = pd.DataFrame({"ct": ["a"] * 8}, index=[str(i) for i in range(8)])
+    with pytest.raises(ValueError, match="reference categories were not found"):
+        cnv.tl.infercnv(_adata(X, var, obs), reference_key="ct", reference_cat=["a", "zzz"])
+
+
+def test_layer_equals_x():
+    # /root/reference/tests/test_tools.py:221-239
+    var = cnv.datasets.synthetic_var(2400, seed=0)
+    X = cnv.datasets.synthetic_counts(64, 2400, seed=5)
+    a = cnv.AnnData(np.zeros_like(X), var=var, layers={"LogNormalize": X})
+    b = cnv.AnnData(X, var=var)
+    cnv.tl.infercnv(a, layer="LogNormalize")
+    cnv.tl.infercnv(b)
+    assert (a.obsm["X_cnv"] != b.obsm["X_cnv"]).nnz == 0
+
+
+# ---- size-independent properties at (close to) bench shape ----------------------------------------
+def test_properties_at_scale():
+    torch = _torch()
+    from infercnvpy_b200._engine import DevicePlan
+    from infercnvpy_b200._layout import build_layout
+
+    dev = torch.device("cuda", 0)
+    G, N, chunk = 20000, 12000, 5000
+    var = cnv.datasets.synthetic_var(G, seed=0)
+    Xd = cnv.datasets.device_counts(N, G, dev, seed=1234)
+    layout = build_layout(var, 100, 10)
+    with DevicePlan(layout, dev) as plan:
+        assert plan.K == 1792 and plan.tier == 0
+        sums, counts = plan.colsum(Xd)
+        ref = plan.mean_from_sums(sums, counts)
+        plan.set_reference(ref)
+        out, stats = plan.smooth(Xd, 3.0)
+        pre = out.clone()
+        thr, row_abs, row_nnz = plan.threshold(out, stats, chunk, 1.5)
+        # (1) every row of the pre-threshold matrix has median 0 (even K: mean of the middle pair)
+        med = pre.double().median(dim=1).values  # lower median
+        srt = pre.double().sort(dim=1).values
+        mid = 0.5 * (srt[:, plan.K // 2 - 1] + srt[:, plan.K // 2])
+        assert float(mid.abs().max()) < 1e-7
+        # (2) per-chunk threshold equals dyn * population std of the chunk
+        for c in range(3):
+            blk = pre[c * chunk : (c + 1) * chunk].double()
+            want = 1.5 * blk.std(unbiased=False).item()
+            assert abs(thr[c].item() - want) / want < 1e-6
+            kept = out[c * chunk : (c + 1) * chunk]
+            assert float(kept[kept != 0].abs().min()) >= thr[c].item() * (1 - 1e-6)
+        # (3) statistics rows
+        np.testing.assert_allclose(row_abs.cpu().numpy(), out.double().abs().sum(dim=1).cpu().numpy(), rtol=1e-12)
+        assert torch.equal(row_nnz.long(), (out != 0).sum(dim=1))
+        # (4) row-shard invariance: two shards cut at a chunk boundary give the same matrix
+        o1, s1 = plan.smooth(Xd[:5000], 3.0)
+        o2, s2 = plan.smooth(Xd[5000:], 3.0)
+        assert torch.equal(torch.cat([o1, o2]), pre)
+        # (5) CSR input (densify on load) == dense input
+        sub = Xd[:3000]
+        csr = sub.to_sparse_csr()
+        o3, _ = plan.smooth((csr.crow_indices().to(torch.int64), csr.col_indices().to(torch.int32), csr.values()), 3.0)
+        assert torch.equal(o3, pre[:3000])
+        # (6) CSR conversion round trip
+        indptr, indices, data = plan.to_csr(out, row_nnz)
+        back = torch.sparse_csr_tensor(indptr, indices.long(), data, size=out.shape).to_dense()
+        assert torch.equal(back, out)
+    # (7) permuting the gene columns together with var leaves the result unchanged
+    perm = np.random.default_rng(0).permutation(G)
+    var_p = var.iloc[perm]
+    layout_p = build_layout(var_p, 100, 10)
+    with DevicePlan(layout_p, dev) as plan_p:
+        plan_p.set_reference(ref[:, torch.from_numpy(perm).to(dev)].contiguous())
+        o4, _ = plan_p.smooth(Xd[:2000][:, torch.from_numpy(perm).to(dev)].contiguous(), 3.0)
+    assert torch.equal(o4, pre[:2000])
+
+
+def test_cnv_score_known_answer_and_golden(golden_loader):
+    # /root/reference/tests/test_scores.py:18-21
+    X_cnv = np.array([[1, 1, 1, 2, 2, 1, 1, 1], [2, 2, 2, 1, 1, 2, 2, 2], [4, 4, 4, 2, 2, 3, 3, 3], [2, 2, 2, 4, 4, 4, 4, 4]]).T
+    obs = pd.DataFrame({"group": list("AAAAABBB")}, index=[f"c{i}" for i in range(8)])
+    for container in (np.array, sp.csr_matrix, sp.csc_matrix):
+        a = cnv.AnnData(np.zeros((8, 3)), obs=obs.copy(), obsm={"X_cnv": container(X_cnv)})
+        res = cnv.tl.cnv_score(a, "group", inplace=False)
+        assert res["A"] == pytest.approx(2.25, abs=1e-3) and res["B"] == pytest.approx(2.5, abs=1e-3)
+        cnv.tl.cnv_score(a, "group")
+        np.testing.assert_allclose(a.obs["cnv_score"].values, [2.25] * 5 + [2.5] * 3)
+    with pytest.raises(ValueError, match="cnv_leiden"):
+        cnv.tl.cnv_score(cnv.AnnData(np.zeros((8, 3)), obs=obs.copy(), obsm={"X_cnv": X_cnv}))
+    gold = golden_loader("small_default")
+    obs = pd.DataFrame({"grp": gold["score_labels"]})
+    a = cnv.AnnData(np.zeros((gold["csr"].shape[0], 1)), obs=obs, obsm={"X_cnv": gold["csr"]})
+    res = cnv.tl.cnv_score(a, "grp", inplace=False)
+    for k, v in zip(gold["score_keys"].tolist(), gold["score_vals"].tolist()):
+        assert float(res[k]) == pytest.approx(v, rel=1e-12)

@@ -1,0 +1,44 @@
+"""Developer timing of the individual kernels (not the driver bench). Usage: python tools/quick_bench.py [N]"""
+import sys, json, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+import infercnvpy_b200 as cnv
+from infercnvpy_b200._engine import DevicePlan
+from infercnvpy_b200._layout import build_layout
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
+G = 20000
+dev = torch.device("cuda", 0)
+var = cnv.datasets.synthetic_var(G, seed=0)
+Xd = cnv.datasets.device_counts(N, G, dev, seed=1000)
+peak = json.load(open(Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"))["hbm_gbs"] if (Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").exists() else 6650.0
+
+def timeit(fn, reps=5, warm=2):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), float(np.median(ts))
+
+for window in (100, 250):
+    layout = build_layout(var, window, 10)
+    with DevicePlan(layout, dev) as plan:
+        info = plan.launch_info()
+        K = plan.K
+        t_cs = timeit(lambda: plan.colsum(Xd))
+        sums, counts = plan.colsum(Xd)
+        ref = plan.mean_from_sums(sums, counts)
+        plan.set_reference(ref)
+        out = torch.empty((N, K), dtype=torch.float32, device=dev)
+        stats = torch.empty((N, 2), dtype=torch.float64, device=dev)
+        t_sm = timeit(lambda: plan.smooth(Xd, 3.0, out=out, row_stats=stats))
+        t_th = timeit(lambda: plan.threshold(out, stats, 5000, 1.5))
+        by = N * (4 * G + 4 * K)
+        print(json.dumps(dict(window=window, N=N, K=K, launch=info,
+              colsum_ms=t_cs, colsum_GBs=N*G*4/t_cs[0]/1e6,
+              smooth_ms=t_sm, smooth_GBs=by/t_sm[0]/1e6, smooth_frac=by/t_sm[0]/1e6/peak, cells_per_s=N/t_sm[0]*1e3,
+              thr_ms=t_th, thr_GBs=2*N*K*4/t_th[0]/1e6)))
