@@ -2,6 +2,7 @@
 import sys, json, time
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import os
 import numpy as np, torch
 import infercnvpy_b200 as cnv
 from infercnvpy_b200._engine import DevicePlan
@@ -14,7 +15,9 @@ var = cnv.datasets.synthetic_var(G, seed=0)
 Xd = cnv.datasets.device_counts(N, G, dev, seed=1000)
 peak = json.load(open(Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"))["hbm_gbs"] if (Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").exists() else 6650.0
 
-def timeit(fn, reps=5, warm=2):
+def timeit(fn, reps=None, warm=2):
+    reps = reps or REPS
+    warm = min(warm, reps)
     for _ in range(warm): fn()
     torch.cuda.synchronize()
     ts = []
@@ -24,7 +27,9 @@ def timeit(fn, reps=5, warm=2):
         ts.append(a.elapsed_time(b))
     return min(ts), float(np.median(ts))
 
-for window in (100, 250):
+WINDOWS = [int(w) for w in os.environ.get("QB_WINDOWS", "100,250").split(",")]
+REPS = int(os.environ.get("QB_REPS", "5"))
+for window in WINDOWS:
     layout = build_layout(var, window, 10)
     with DevicePlan(layout, dev) as plan:
         info = plan.launch_info()
