@@ -73,9 +73,9 @@ struct icnv_plan {
     int base_tier = 2;
     int32_t gs = 0, NG = 0, NGpad = 0, NQ = 0, qstar = -1, Gpad = 0;
     int32_t n_tasks_g = 0;
-    DevBuf<uint16_t> idx_t;
-    DevBuf<int32_t> cols_t;  // same layout as idx_t, int32, pad = -1 (input of the bounds kernel)
-    DevBuf<float> lo_t, hi_t;
+    DevBuf<uint32_t> off_w;  // [warp-block][j][lane][u] byte offsets into the staged row
+    DevBuf<int32_t> cols_w;  // same layout, column index, pad = -1 (input of the bounds kernel)
+    DevBuf<float> lo_w, hi_w;
     DevBuf<double> alpha, beta, cw;
     DevBuf<Task> tasks_g;
 
@@ -95,10 +95,10 @@ struct icnv_plan {
     DevBuf<double> colsum_partial;
 
     ~icnv_plan() {
-        idx_t.release();
-        cols_t.release();
-        lo_t.release();
-        hi_t.release();
+        off_w.release();
+        cols_w.release();
+        lo_w.release();
+        hi_w.release();
         alpha.release();
         beta.release();
         cw.release();
@@ -145,7 +145,7 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
             *c = {0, p.window, p.gs, 1, smem_grouped(p, 0)};
             return 0;
         }
-        if (smem_grouped(p, 1) <= SMEM_MAX && p.n_tasks_g <= 4 * NT) {
+        if (smem_grouped(p, 1) <= SMEM_MAX && p.n_tasks_g <= 4 * NT) {  // TPT 1 or 4
             *c = {1, 0, 0, p.n_tasks_g <= NT ? 1 : 4, smem_grouped(p, 1)};
             return 0;
         }
@@ -155,12 +155,12 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
                   std::to_string(p.n_sorted) + " genes" + (c64 ? ", float64 centring)" : ")"));
         return ICNV_EUNSUPPORTED;
     }
-    if (p.n_tasks_d > 8 * NT) {
+    if (p.n_tasks_d > 4 * NT) {
         set_error("output too wide for the register-resident median: K = " + std::to_string(p.K) + " > " +
-                  std::to_string(8 * NT * LOUT));
+                  std::to_string(4 * NT * LOUT));
         return ICNV_EUNSUPPORTED;
     }
-    *c = {2, 0, 0, p.n_tasks_d <= NT ? 1 : 8, smem_direct(p, c64)};
+    *c = {2, 0, 0, p.n_tasks_d <= NT ? 1 : 4, smem_direct(p, c64)};
     return 0;
 }
 
@@ -244,7 +244,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
     }
 
     // ---- grouped layout: groups of gs = step genes when step | window
-    p->group_ok = (n % s == 0) && (n_genes < 65535);
+    p->group_ok = (n % s == 0) && (n_genes < (1 << 28));
     if (p->group_ok) {
         const int gs = s;
         p->gs = gs;
@@ -259,20 +259,32 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         p->NGpad = (p->NG + 3) / 4 * 4;
         if (p->NGpad == 0) p->NGpad = 4;
         p->Gpad = (n_genes + 1 + 3) / 4 * 4;
-        std::vector<uint16_t> idx((size_t)gs * p->NGpad, (uint16_t)n_genes);
-        std::vector<int32_t> cols((size_t)gs * p->NGpad, -1);
-        for (int c = 0; c < n_seg; ++c) {
-            const int32_t s0 = p->seg_off[c];
-            const int32_t Gc = p->seg_off[c + 1] - s0;
-            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g)
-                for (int j = 0; j < gs; ++j) {
-                    const int32_t pos = (g - gbase[c]) * gs + j;
-                    if (pos < Gc) {
-                        idx[(size_t)j * p->NGpad + g] = (uint16_t)p->gene_idx[s0 + pos];
-                        cols[(size_t)j * p->NGpad + g] = p->gene_idx[s0 + pos];
+        // tables in kernel order: entry ((wb*gs + j)*32 + lane)*4 + u  <->  element j of group u*nquads + wb*32 + lane
+        const int nquads = p->NGpad / 4;
+        const int n_wb = (nquads + 31) / 32;
+        std::vector<int32_t> seg_of_group(p->NG);
+        for (int c = 0; c < n_seg; ++c)
+            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g) seg_of_group[g] = c;
+        const size_t n_entries = (size_t)n_wb * gs * 32 * 4;
+        std::vector<uint32_t> off(n_entries, (uint32_t)n_genes * 4u);
+        std::vector<int32_t> cols(n_entries, -1);
+        for (int wb = 0; wb < n_wb; ++wb)
+            for (int j = 0; j < gs; ++j)
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int u = 0; u < 4; ++u) {
+                        const int quad = wb * 32 + lane;
+                        if (quad >= nquads) continue;
+                        const int32_t g = u * nquads + quad;
+                        if (g >= p->NG) continue;
+                        const int c = seg_of_group[g];
+                        const int32_t s0 = p->seg_off[c];
+                        const int32_t Gc = p->seg_off[c + 1] - s0;
+                        const int32_t pos = (g - gbase[c]) * gs + j;
+                        if (pos >= Gc) continue;
+                        const size_t e = (((size_t)wb * gs + j) * 32 + lane) * 4 + u;
+                        off[e] = (uint32_t)p->gene_idx[s0 + pos] * 4u;
+                        cols[e] = p->gene_idx[s0 + pos];
                     }
-                }
-        }
         // weights: within a group the pyramid is linear in j except (at most) the group holding the peak
         std::vector<double> alpha(p->NQ, 0.0), beta(p->NQ, 0.0), cw(gs, 0.0);
         p->qstar = -1;
@@ -306,10 +318,10 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             }
         }
         p->n_tasks_g = (int32_t)tasks.size();
-        if (p->idx_t.upload(idx) || p->cols_t.upload(cols) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
+        if (p->off_w.upload(off) || p->cols_w.upload(cols) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
             p->cw.upload(cw) || p->tasks_g.upload(tasks))
             return ICNV_ECUDA;
-        if (p->lo_t.alloc(idx.size()) || p->hi_t.alloc(idx.size())) return ICNV_ECUDA;
+        if (p->lo_w.alloc(n_entries) || p->hi_w.alloc(n_entries)) return ICNV_ECUDA;
     }
     if (flat_inv.empty()) flat_inv.push_back(1.0);
     if (p->flat_inv.upload(flat_inv)) return ICNV_ECUDA;
@@ -400,8 +412,8 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
     int rc = choose(*plan, c64, &ch);
     if (rc) return rc;
     if (ch.tier < 2) {
-        rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->cols_t.ptr, (int64_t)plan->cols_t.n, plan->lo_t.ptr,
-                              plan->hi_t.ptr, false, st);
+        rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->cols_w.ptr, (int64_t)plan->cols_w.n, plan->lo_w.ptr,
+                              plan->hi_w.ptr, false, st);
     } else {
         rc = aux_build_bounds(ref, c64, n_cat, plan->G, plan->idx_lin.ptr, plan->n_sorted, plan->lo_lin.ptr,
                               plan->hi_lin.ptr, c64, st);
@@ -438,9 +450,9 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     sp.NGpad = plan->NGpad;
     sp.NQ = plan->NQ;
     sp.qstar = plan->qstar;
-    sp.idx_t = plan->idx_t.ptr;
-    sp.lo_t = plan->lo_t.ptr;
-    sp.hi_t = plan->hi_t.ptr;
+    sp.off_w = plan->off_w.ptr;
+    sp.lo_w = plan->lo_w.ptr;
+    sp.hi_w = plan->hi_w.ptr;
     sp.alpha = plan->alpha.ptr;
     sp.beta = plan->beta.ptr;
     sp.cw = plan->cw.ptr;
@@ -452,6 +464,7 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     sp.hi_lin = plan->hi_lin.ptr;
     sp.wdir = plan->wdir.ptr;
     sp.clip = plan->c64 ? lfc_clip : (double)(float)lfc_clip;
+    sp.clipf = (float)lfc_clip;
     sp.inv_sumw = plan->inv_sumw;
     sp.flat_inv = plan->flat_inv.ptr;
     sp.tasks = ch.tier < 2 ? plan->tasks_g.ptr : plan->tasks_d.ptr;

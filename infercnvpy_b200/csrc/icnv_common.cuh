@@ -10,9 +10,9 @@ namespace icnv {
 
 constexpr int NT = 512;         // threads per CTA of the smoothing kernel
 constexpr int NW = NT / 32;     // warps per CTA
-constexpr int LOUT = 5;         // consecutive outputs owned by one task (odd -> conflict-free smem strides)
+constexpr int LOUT = 9;         // consecutive outputs owned by one task (9*16 B stride -> conflict-free LDS.128)
 constexpr int CAND_CAP = 32;    // median: size of the final exact candidate set
-constexpr int PAD_GROUPS = 8;   // slack groups after the last one (sliding window over-read)
+constexpr int PAD_GROUPS = 12;  // slack groups after the last one (sliding window over-read, >= LOUT)
 
 // pyramid weight j of an n-wide window: min(j + 1, n - j)  (tl/_infercnv.py:206-207)
 __host__ __device__ constexpr int pyr(int n, int j) { return (j + 1) < (n - j) ? (j + 1) : (n - j); }
@@ -44,9 +44,11 @@ struct SmoothParams {
     int32_t NGpad;    // multiple of 4
     int32_t NQ;       // groups per window
     int32_t qstar;    // group-in-window holding the pyramid peak (non-linear weights), -1 if none
-    const uint16_t* idx_t;  // [gs][NGpad] column of X for element j of group g (G = zero pad)
-    const float* lo_t;      // [gs][NGpad] reference lower bound (== ref when one category)
-    const float* hi_t;      // [gs][NGpad] upper bound (only read when BOUNDED)
+    // Per-gene tables in the order the kernel walks them: [warp-block of 32 quads][j < gs][lane][u < 4];
+    // entry (wb, j, lane, u) belongs to element j of group u*(NGpad/4) + wb*32 + lane.
+    const uint32_t* off_w;  // BYTE offset of the gene inside the staged raw row (4*G = zero pad slot)
+    const float* lo_w;      // reference lower bound (== ref when one category)
+    const float* hi_w;      // upper bound (only read when BOUNDED)
     const double* alpha;    // [NQ] weight of A_g = sum_j x
     const double* beta;     // [NQ] weight of B_g = sum_j j*x
     const double* cw;       // [gs] weights inside the peak group (C_g = sum_j cw_j x)
@@ -60,6 +62,7 @@ struct SmoothParams {
     const double* wdir;     // [window] pyramid weights
     // ---- common
     double clip;
+    float clipf;
     double inv_sumw;
     const double* flat_inv; // 1 / (genes of flat segment)
     const Task* tasks;
@@ -113,9 +116,9 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ uint2 ldg_nc_u2(const void* p) {
-    uint2 v;
-    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {

@@ -5,19 +5,21 @@
 // Data flow per row (tiers 0/1, "grouped"):
 //   HBM --cp.async.bulk (TMA, mbarrier)--> smem raw row [G] fp32
 //   phase 2: every thread owns 4 position-ordered groups of `gs` (= step) genes; it gathers its genes
-//            from the raw row through the u16 column table, centres + clips in fp32 exactly like
-//            numpy, and accumulates per-group partial sums in fp64:
+//            from the raw row through a pre-scaled byte-offset table (warp-coalesced 16-byte table
+//            loads, immediate offsets), centres + clips in fp32 exactly like numpy, and accumulates
+//            per-group partial sums in fp64:
 //              A_g = sum_j x_j,  B_g = sum_j j*x_j,  C_g = sum_j cw_j*x_j (peak group only)
 //            Within a step-aligned group the pyramid weights are linear in j, so every window is
 //              out_k = sum_q alpha_q*A_{k+q} + beta_q*B_{k+q}  (+ C_{k+q*})
 //            i.e. 2*window/step FMAs instead of `window` — and nothing is computed for the 90 % of
 //            windows the reference computes and then drops (:215-218).
-//   phase 3: one thread per LOUT=5 consecutive outputs slides over the partials (fp64 FMAs, weights
-//            are compile-time immediates in tier 0).
+//   phase 3: one thread per LOUT=9 consecutive outputs slides over the partials (fp64 FMAs, weights
+//            are compile-time immediates in tier 0), and accumulates the row's sum / sum of squares.
 //   median : exact selection on order-preserving 32-bit keys held in registers: 8-bin counting
-//            passes with packed counters + warp REDUX, then an exact fp64 ranking of <= 32
+//            passes with packed 4-bit counters + warp REDUX (one barrier per pass, every warp
+//            derives the next bracket redundantly), then an exact fp64 ranking of <= 32
 //            candidates (np.median semantics: mean of the two middle values for even K).
-//   write  : out[row, :] = v - median (fp32 or fp64) and the row's sum / sum of squares (fp64).
+//   write  : out[row, :] = v - median (fp32 or fp64); row statistics follow from the sums.
 // Tier 2 ("direct") evaluates the reference formula literally from a position-sorted centred row in
 // smem; it covers every (window, step) and float64 centring and is the slow general fallback.
 #include "icnv_common.cuh"
@@ -25,30 +27,19 @@
 namespace icnv {
 
 struct __align__(16) Scratch {
-    uint4 wcnt[NW];
+    uint4 wcnt[2][NW];
     double wred[NW][2];
     double cand[CAND_CAP];
     double med[2];
-    float wsum[NW][2];
     unsigned long long mbar;
-    uint32_t klo;
-    uint32_t ksplit;
-    int shift;
-    int below;
-    int state;
     int cand_n;
     int bcnt[NW];
     int btotal;
+    int next_wb[2];  // phase-2 work stealing: next warp-block of quads, per row parity
 };
 constexpr int SCRATCH_BYTES = (sizeof(Scratch) + 15) / 16 * 16;
 
-
 __device__ __forceinline__ double warp_sum_d(double x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-}
-__device__ __forceinline__ float warp_sum_f(float x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
@@ -64,17 +55,26 @@ __device__ __forceinline__ double warp_min_d(double x) {
     return x;
 }
 
-// total of a per-thread int over the CTA, returned to every thread (2 barriers)
-__device__ __forceinline__ int block_count(int local, Scratch* sc, int lane, int warp) {
+// barrier 1 over the first `nthreads` threads of the CTA (the warps that own output values); the other
+// warps never touch it and run ahead into the next row
+__device__ __forceinline__ void group_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// total of a per-thread int over the group, returned to every thread (2 barriers; slow path only)
+__device__ __noinline__ int block_count(int local, Scratch* sc, int lane, int warp, int nthreads) {
     int w = __reduce_add_sync(0xffffffffu, local);
     if (lane == 0) sc->bcnt[warp] = w;
-    __syncthreads();
+    group_sync(nthreads);
     if (warp == 0) {
-        int t = lane < NW ? sc->bcnt[lane] : 0;
+        int t = lane < (nthreads >> 5) ? sc->bcnt[lane] : 0;
         t = __reduce_add_sync(0xffffffffu, t);
         if (lane == 0) sc->btotal = t;
     }
-    __syncthreads();
+    group_sync(nthreads);
     return sc->btotal;
 }
 
@@ -83,56 +83,40 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// Exact median of the K values spread over the CTA's registers (np.median semantics,
-// /root/reference/src/infercnvpy/tl/_infercnv.py:442).  Every thread gets the result.
-template <int TPT>
-__device__ double block_median(const double (&v)[TPT * LOUT], const int (&nv)[TPT], int K, Scratch* sc, int lane,
-                               int warp) {
-    // ---- location / scale guess in fp32 (only steers the bracket; exactness never depends on it)
-    float s1 = 0.f, s2 = 0.f;
+// Exact median of the K finite values spread over the CTA's registers (np.median semantics,
+// /root/reference/src/infercnvpy/tl/_infercnv.py:442).  Unused slots hold +inf (they sort last and
+// never reach the middle ranks).  S1 / S2 = sum and sum of squares of the K values, known to every
+// thread; they only steer the first bracket — exactness never depends on them.  Returns the median to
+// every thread.  Must be called by exactly the first `nthreads` threads of the CTA (whole warps).
+template <int VPT>
+__device__ double block_median(const double (&v)[VPT], int K, double S1, double S2, Scratch* sc, int lane, int warp,
+                               int nthreads) {
+    const int nwarps = nthreads >> 5;
+    // the median lies within one standard deviation of the mean; 2 % slack for the fp32 arithmetic
+    const float invK = 1.f / (float)K;
+    const float mean = (float)S1 * invK;
+    const float var = fmaxf((float)S2 * invK - mean * mean, 0.f);
+    const float half = fmaxf(1.02f * sqrtf(var) + 1e-6f * fabsf(mean), 1e-20f);
+    const double kbase = (double)(mean - half);
+    const double kscale = (double)(2147483648.f / half);
+    // key(v) = saturating floor((v - kbase) * kscale): monotone in v, 32 bits; +inf -> 0xFFFFFFFF
+    uint32_t key[VPT];
 #pragma unroll
-    for (int tt = 0; tt < TPT; ++tt)
-#pragma unroll
-        for (int i = 0; i < LOUT; ++i)
-            if (i < nv[tt]) {
-                float f = (float)v[tt * LOUT + i];
-                s1 += f;
-                s2 = fmaf(f, f, s2);
-            }
-    s1 = warp_sum_f(s1);
-    s2 = warp_sum_f(s2);
-    if (lane == 0) {
-        sc->wsum[warp][0] = s1;
-        sc->wsum[warp][1] = s2;
-    }
-    __syncthreads();
-    float t1 = lane < NW ? sc->wsum[lane][0] : 0.f;
-    float t2 = lane < NW ? sc->wsum[lane][1] : 0.f;
-    t1 = warp_sum_f(t1);
-    t2 = warp_sum_f(t2);
-    const double mean = (double)t1 / (double)K;
-    const double var = fmax((double)t2 / (double)K - mean * mean, 0.0);
-    // the median lies within one standard deviation of the mean; 2 % slack for the fp32 sums
-    const double half = 1.02 * sqrt(var) + 1e-6 * fabs(mean) + 1e-30;
-    const double kbase = mean - half;
-    const double kscale = 4294967296.0 / (2.0 * half);
-    // key(v) = saturating floor((v - kbase) * kscale): monotone in v, 32 bits
-#define ICNV_KEY(x) __double2uint_rd(((x)-kbase) * kscale)
+    for (int i = 0; i < VPT; ++i) key[i] = __double2uint_rd((v[i] - kbase) * kscale);
 
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
-    uint32_t klo = 0;
-    int shift = 29, below = 0, state = 0;
+    uint32_t klo = 0, ksplit = 0;
+    int shift = 29, below = 0, state = 0, buf = 0;
     while (true) {
         uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;  // 16-bit fields: bins (0,1) (2,3) (4,5) (6,7)
 #pragma unroll
-        for (int tt = 0; tt < TPT; ++tt) {
+        for (int g0 = 0; g0 < VPT; g0 += LOUT) {
             uint32_t c4 = 0;  // eight 4-bit counters (<= LOUT each)
 #pragma unroll
-            for (int i = 0; i < LOUT; ++i)
-                if (i < nv[tt]) {
-                    uint32_t b = (ICNV_KEY(v[tt * LOUT + i]) - klo) >> shift;
-                    if (b < 8u) c4 += 1u << (4u * b);
-                }
+            for (int i = g0; i < g0 + LOUT; ++i) {
+                const uint32_t b = (key[i] - klo) >> shift;
+                c4 += (b < 8u) ? (1u << (4u * b)) : 0u;
+            }
             w0 += (c4 & 0xFu) | ((c4 & 0xF0u) << 12);
             w1 += ((c4 >> 8) & 0xFu) | ((c4 & 0xF000u) << 4);
             w2 += ((c4 >> 16) & 0xFu) | ((c4 >> 4) & 0xF0000u);
@@ -142,79 +126,64 @@ __device__ double block_median(const double (&v)[TPT * LOUT], const int (&nv)[TP
         w1 = __reduce_add_sync(0xffffffffu, w1);
         w2 = __reduce_add_sync(0xffffffffu, w2);
         w3 = __reduce_add_sync(0xffffffffu, w3);
-        if (lane == 0) sc->wcnt[warp] = make_uint4(w0, w1, w2, w3);
-        __syncthreads();
-        if (warp == 0) {
-            uint4 c = lane < NW ? sc->wcnt[lane] : make_uint4(0, 0, 0, 0);
-            c.x = __reduce_add_sync(0xffffffffu, c.x);
-            c.y = __reduce_add_sync(0xffffffffu, c.y);
-            c.z = __reduce_add_sync(0xffffffffu, c.z);
-            c.w = __reduce_add_sync(0xffffffffu, c.w);
-            if (lane == 0) {
-                int cnt[8] = {(int)(c.x & 0xFFFF), (int)(c.x >> 16), (int)(c.y & 0xFFFF), (int)(c.y >> 16),
-                              (int)(c.z & 0xFFFF), (int)(c.z >> 16), (int)(c.w & 0xFFFF), (int)(c.w >> 16)};
-                int cum = below, b1 = -1, b2 = -1, below1 = below;
+        if (lane == 0) sc->wcnt[buf][warp] = make_uint4(w0, w1, w2, w3);
+        group_sync(nthreads);
+        // every warp derives the decision itself (no second barrier): lane b < 8 owns bin b
+        uint4 c = lane < nwarps ? sc->wcnt[buf][lane] : make_uint4(0, 0, 0, 0);
+        buf ^= 1;
+        c.x = __reduce_add_sync(0xffffffffu, c.x);
+        c.y = __reduce_add_sync(0xffffffffu, c.y);
+        c.z = __reduce_add_sync(0xffffffffu, c.z);
+        c.w = __reduce_add_sync(0xffffffffu, c.w);
+        const uint32_t word = (lane & 4) ? ((lane & 2) ? c.w : c.z) : ((lane & 2) ? c.y : c.x);
+        const int cb = lane < 8 ? (int)((lane & 1) ? (word >> 16) : (word & 0xFFFFu)) : 0;
+        int incl = cb;
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    if (b1 < 0 && cum + cnt[b] > r1) {
-                        b1 = b;
-                        below1 = cum;
-                    }
-                    if (b2 < 0 && cum + cnt[b] > r2) b2 = b;
-                    cum += cnt[b];
-                }
-                int st;
-                if (b1 < 0 || b2 < 0) {  // cannot happen for finite input; fall back to the exact path
-                    st = 3;
-                    sc->klo = 0;
-                    sc->shift = 32;
-                    sc->below = 0;
-                } else if (b1 == b2) {
-                    const int n_in = cnt[b1];
-                    sc->klo = klo + ((uint32_t)b1 << shift);
-                    sc->below = below1;
-                    if (n_in <= CAND_CAP) {
-                        st = 1;
-                        sc->shift = shift;
-                    } else if (shift == 0) {
-                        st = 3;
-                        sc->shift = 0;
-                    } else {
-                        st = 0;
-                        sc->shift = shift >= 3 ? shift - 3 : 0;
-                    }
-                } else {
-                    st = 2;
-                    sc->ksplit = klo + ((uint32_t)b2 << shift);
-                }
-                sc->state = st;
-                sc->cand_n = 0;
-            }
+        for (int o = 1; o < 8; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        __syncthreads();
-        state = sc->state;
-        if (state == 2) break;
-        klo = sc->klo;
-        shift = sc->shift;
-        below = sc->below;
-        if (state != 0) break;
+        incl += below;
+        const unsigned m1 = __ballot_sync(0xffffffffu, lane < 8 && incl > r1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, lane < 8 && incl > r2);
+        const int b1 = __ffs(m1) - 1, b2 = __ffs(m2) - 1;
+        const int below1 = __shfl_sync(0xffffffffu, incl - cb, b1 & 31);
+        const int n_in = __shfl_sync(0xffffffffu, cb, b1 & 31);
+        if (b1 < 0 || b2 < 0) {  // cannot happen for finite input; take the exact slow path over everything
+            state = 3;
+            klo = 0;
+            shift = 32;
+            below = 0;
+            break;
+        }
+        if (b1 != b2) {
+            state = 2;
+            ksplit = klo + ((uint32_t)b2 << shift);
+            break;
+        }
+        klo += (uint32_t)b1 << shift;
+        below = below1;
+        if (n_in <= CAND_CAP) {
+            state = 1;
+            break;
+        }
+        if (shift == 0) {
+            state = 3;
+            break;
+        }
+        shift = shift >= 3 ? shift - 3 : 0;
     }
 
     double m;
     if (state == 1) {
         // <= CAND_CAP values share the final key range: rank them exactly in fp64
 #pragma unroll
-        for (int tt = 0; tt < TPT; ++tt)
-#pragma unroll
-            for (int i = 0; i < LOUT; ++i)
-                if (i < nv[tt]) {
-                    const double x = v[tt * LOUT + i];
-                    if (((ICNV_KEY(x) - klo) >> shift) == 0u) {
-                        int slot = atomicAdd(&sc->cand_n, 1);
-                        sc->cand[slot] = x;
-                    }
-                }
-        __syncthreads();
+        for (int i = 0; i < VPT; ++i)
+            if (((key[i] - klo) >> shift) == 0u) {
+                const int slot = atomicAdd(&sc->cand_n, 1);
+                sc->cand[slot] = v[i];
+            }
+        group_sync(nthreads);
         if (warp == 0) {
             const int n = sc->cand_n;
             const double mine = lane < n ? sc->cand[lane] : 0.0;
@@ -228,40 +197,34 @@ __device__ double block_median(const double (&v)[TPT * LOUT], const int (&nv)[TP
                 if (rank == r2 - below) sc->med[1] = mine;
             }
         }
-        __syncthreads();
+        group_sync(nthreads);
         m = (sc->med[0] + sc->med[1]) / 2.0;
     } else if (state == 2) {
         // the two middle ranks sit on either side of a bin boundary
-        const uint32_t ks = sc->ksplit;
         double lo = -INFINITY, hi = INFINITY;
 #pragma unroll
-        for (int tt = 0; tt < TPT; ++tt)
-#pragma unroll
-            for (int i = 0; i < LOUT; ++i)
-                if (i < nv[tt]) {
-                    const double x = v[tt * LOUT + i];
-                    if (ICNV_KEY(x) < ks)
-                        lo = fmax(lo, x);
-                    else
-                        hi = fmin(hi, x);
-                }
+        for (int i = 0; i < VPT; ++i) {
+            if (key[i] < ksplit)
+                lo = fmax(lo, v[i]);
+            else
+                hi = fmin(hi, v[i]);
+        }
         lo = warp_max_d(lo);
         hi = warp_min_d(hi);
         if (lane == 0) {
             sc->wred[warp][0] = lo;
             sc->wred[warp][1] = hi;
         }
-        __syncthreads();
-        lo = lane < NW ? sc->wred[lane][0] : -INFINITY;
-        hi = lane < NW ? sc->wred[lane][1] : INFINITY;
+        group_sync(nthreads);
+        lo = lane < nwarps ? sc->wred[lane][0] : -INFINITY;
+        hi = lane < nwarps ? sc->wred[lane][1] : INFINITY;
         lo = warp_max_d(lo);
         hi = warp_min_d(hi);
         m = (lo + hi) / 2.0;
-        __syncthreads();  // wred is reused by the caller
     } else {
         // more than CAND_CAP values collapse onto one 32-bit key (ties / degenerate rows):
         // exact radix select on the order-preserving 64-bit pattern, one bit per step
-        double res[2];
+        double res[2] = {0.0, 0.0};
         for (int which = 0; which < 2; ++which) {
             if (which == 1 && r2 == r1) {
                 res[1] = res[0];
@@ -272,19 +235,13 @@ __device__ double block_median(const double (&v)[TPT * LOUT], const int (&nv)[TP
             for (int bit = 63; bit >= 0; --bit) {
                 int local = 0;
 #pragma unroll
-                for (int tt = 0; tt < TPT; ++tt)
-#pragma unroll
-                    for (int i = 0; i < LOUT; ++i)
-                        if (i < nv[tt]) {
-                            const double x = v[tt * LOUT + i];
-                            const bool in_set = shift >= 32 ? true : (((ICNV_KEY(x) - klo) >> shift) == 0u);
-                            if (in_set) {
-                                const unsigned long long ob = ordered_bits(x);
-                                const bool same_prefix = bit == 63 ? true : ((ob >> (bit + 1)) == (prefix >> (bit + 1)));
-                                local += same_prefix && !((ob >> bit) & 1ull);
-                            }
-                        }
-                const int zeros = block_count(local, sc, lane, warp);
+                for (int i = 0; i < VPT; ++i) {
+                    const bool in_set = shift >= 32 ? true : (((key[i] - klo) >> shift) == 0u);
+                    const unsigned long long ob = ordered_bits(v[i]);
+                    const bool same_prefix = bit == 63 ? true : ((ob >> (bit + 1)) == (prefix >> (bit + 1)));
+                    local += in_set && same_prefix && !((ob >> bit) & 1ull);
+                }
+                const int zeros = block_count(local, sc, lane, warp, nthreads);
                 if (rr >= zeros) {
                     rr -= zeros;
                     prefix |= 1ull << bit;
@@ -295,7 +252,6 @@ __device__ double block_median(const double (&v)[TPT * LOUT], const int (&nv)[TP
         }
         m = (res[0] + res[1]) / 2.0;
     }
-#undef ICNV_KEY
     return m;
 }
 
@@ -309,9 +265,10 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr bool GROUPED = TIER < 2;
     constexpr int NQ_C = (TIER == 0) ? NWIN / GS : 0;
-    constexpr bool M3_C = (TIER == 0) && ((NWIN % 2 == 0) ? ((NWIN / 2) % GS != 0) : (GS > 1));
+    constexpr bool M3_C = (TIER == 0) && ((NWIN / 2) % GS != 0);
     constexpr int QSTAR_C = M3_C ? (NWIN / 2) / GS : -1;
     static_assert(TIER != 0 || NWIN % 2 == 0, "tier 0 instantiations use even windows");
+    constexpr int VPT = TPT * LOUT;
 
     // ---- carve shared memory
     float* raw = nullptr;
@@ -370,6 +327,11 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     } else {
         for (int i = tid; i < p.window; i += NT) wdir[i] = p.wdir[i];
     }
+    if (tid == 0) {
+        sc->next_wb[0] = 0;
+        sc->next_wb[1] = 0;
+        sc->cand_n = 0;
+    }
     __syncthreads();
 
     const uint64_t pol = l2_policy_evict_first();
@@ -387,10 +349,18 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     const bool tma = GROUPED && dense && p.use_tma;
     if (tma && tid == 0 && row < p.n_rows) issue_row(row);
 
-    const float clipf = (float)p.clip;
+    const float clipf = p.clipf;
     const int nquads = p.NGpad >> 2;
+    const int n_wb = (nquads + 31) >> 5;
+    const double Kd = (double)p.K;
+    const uint32_t raw_s = GROUPED ? smem_u32(raw) : 0u;
+    // Only the warps that own output values ("group") take part in phase 3 / median / write-out; the others
+    // go straight to the next row and work ahead on its gathers (barrier 1 = group only, barrier 0 = CTA).
+    const int n_group = min(NT, ((p.n_tasks + 31) >> 5) << 5);
+    const bool in_group = tid < n_group;
+    int it = 0;
 
-    for (; row < p.n_rows; row += gridDim.x) {
+    for (; row < p.n_rows; row += gridDim.x, ++it) {
         // ======================= stage the raw row =======================
         if constexpr (GROUPED) {
             if (tma) {
@@ -413,17 +383,28 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
 
         // ======================= centre + clip + partial sums =======================
         if constexpr (GROUPED) {
-            for (int quad = tid; quad < nquads; quad += NT) {
+            // warp-blocks of 32 quads are handed out dynamically: warps that are not in the group arrive
+            // here early (they skipped the median of the previous row) and take most of them
+            int* next_wb = &sc->next_wb[it & 1];
+            while (true) {
+                int wb = 0;
+                if (lane == 0) wb = atomicAdd(next_wb, 1);
+                wb = __shfl_sync(0xffffffffu, wb, 0);
+                if (wb >= n_wb) break;
+                const int quad = (wb << 5) + lane;
+                if (quad >= nquads) continue;
                 double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
-                const uint16_t* ip = p.idx_t + 4 * quad;
-                const float* lp = p.lo_t + 4 * quad;
-                const float* hp = p.hi_t + 4 * quad;
+                // table entry (wb, j, lane, u): ((wb*gs + j)*32 + lane)*4 + u
+                const size_t tbase = ((size_t)wb * gs * 32 + lane) * 4;
+                const uint32_t* ip = p.off_w + tbase;
+                const float* lp = p.lo_w + tbase;
+                const float* hp = p.hi_w + tbase;
                 auto body = [&](int j, double cwj) {
-                    const uint2 id = ldg_nc_u2(ip + (size_t)j * p.NGpad);
-                    const float4 lo = ldg_nc_f4(lp + (size_t)j * p.NGpad);
+                    const uint4 id = ldg_nc_u4(ip + j * 128);
+                    const float4 lo = ldg_nc_f4(lp + j * 128);
                     float4 hi = lo;
-                    if constexpr (BOUNDED) hi = ldg_nc_f4(hp + (size_t)j * p.NGpad);
-                    const float x[4] = {raw[id.x & 0xFFFFu], raw[id.x >> 16], raw[id.y & 0xFFFFu], raw[id.y >> 16]};
+                    if constexpr (BOUNDED) hi = ldg_nc_f4(hp + j * 128);
+                    const float x[4] = {lds_f32(raw_s + id.x), lds_f32(raw_s + id.y), lds_f32(raw_s + id.z), lds_f32(raw_s + id.w)};
                     const float l4[4] = {lo.x, lo.y, lo.z, lo.w};
                     const float h4[4] = {hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
@@ -436,7 +417,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                         d = fminf(fmaxf(d, -clipf), clipf);
                         const double dd = (double)d;
                         a[u] += dd;
-                        b[u] = fma((double)j, dd, b[u]);
+                        if (j > 0) b[u] = fma((double)j, dd, b[u]);
                         if (qstar >= 0) c[u] = fma(cwj, dd, c[u]);
                     }
                 };
@@ -446,14 +427,18 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 } else {
                     for (int j = 0; j < gs; ++j) body(j, w_c[j]);
                 }
+                // thread's u-th group is u*nquads + quad: for fixed u the lanes store consecutive 16 B
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    AB[4 * quad + u] = make_double2(a[u], b[u]);
-                    if (qstar >= 0) Cp[4 * quad + u] = c[u];
+                    AB[u * nquads + quad] = make_double2(a[u], b[u]);
+                    if (qstar >= 0) Cp[u * nquads + quad] = c[u];
                 }
             }
             __syncthreads();  // gathers done: raw row is dead, partials visible
-            if (tma && tid == 0 && row + gridDim.x < p.n_rows) issue_row(row + gridDim.x);
+            if (tid == 0) {
+                *next_wb = 0;  // used again two rows from now
+                if (tma && row + gridDim.x < p.n_rows) issue_row(row + gridDim.x);
+            }
         } else {
             // direct tier: position-sorted centred row (float, or double for float64 centring)
             for (int s = tid; s < p.n_sorted; s += NT) {
@@ -487,17 +472,25 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
             __syncthreads();
         }
 
+        if (!in_group) {
+            __syncthreads();  // partials / sorted row consumed by the group: safe to start the next row
+            continue;
+        }
+
         // ======================= windows =======================
-        double v[TPT * LOUT];
-        int nv[TPT];
+        double v[VPT];
+        int nv[TPT], col0[TPT];
+        double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
             nv[tt] = 0;
+            col0[tt] = 0;
 #pragma unroll
-            for (int i = 0; i < LOUT; ++i) v[tt * LOUT + i] = 0.0;
+            for (int i = 0; i < LOUT; ++i) v[tt * LOUT + i] = INFINITY;
             const int ti = tid + tt * NT;
             if (ti < p.n_tasks) {
-                const Task t = p.tasks[ti];
+                const int4 t = __ldg(reinterpret_cast<const int4*>(p.tasks) + ti);
+                col0[tt] = t.y;
                 if ((t.w & 0xFF) == 0) {
                     nv[tt] = t.z;
                     if constexpr (TIER == 0) {
@@ -527,7 +520,8 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                             for (int i = 0; i < LOUT; ++i) acc[i] += Cp[t.x + QSTAR_C + i];
                         }
 #pragma unroll
-                        for (int i = 0; i < LOUT; ++i) v[tt * LOUT + i] = acc[i] * p.inv_sumw;
+                        for (int i = 0; i < LOUT; ++i)
+                            if (i < t.z) v[tt * LOUT + i] = acc[i] * p.inv_sumw;
                     } else if constexpr (TIER == 1) {
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i) {
@@ -573,48 +567,52 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                     }
                     v[tt * LOUT] = acc * p.flat_inv[t.w >> 8];
                 }
-            }
-        }
-
-        // ======================= row median, centring, statistics =======================
-        const double m = block_median<TPT>(v, nv, p.K, sc, lane, warp);
-        double s = 0.0, ss = 0.0;
-#pragma unroll
-        for (int tt = 0; tt < TPT; ++tt) {
-            const int ti = tid + tt * NT;
-            if (ti < p.n_tasks) {
-                const int col0 = p.tasks[ti].y;
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i)
                     if (i < nv[tt]) {
-                        const double x = v[tt * LOUT + i] - m;
-                        s += x;
-                        ss = fma(x, x, ss);
-                        if (p.out_f64)
-                            reinterpret_cast<double*>(p.out)[row * p.ldo + col0 + i] = x;
-                        else
-                            reinterpret_cast<float*>(p.out)[row * p.ldo + col0 + i] = (float)x;
+                        const double x = v[tt * LOUT + i];
+                        s1 += x;
+                        s2 = fma(x, x, s2);
                     }
             }
         }
-        s = warp_sum_d(s);
-        ss = warp_sum_d(ss);
+
+        // ======================= row sums (one fp64 reduction), median, centring =======================
+        s1 = warp_sum_d(s1);
+        s2 = warp_sum_d(s2);
         if (lane == 0) {
-            sc->wred[warp][0] = s;
-            sc->wred[warp][1] = ss;
+            sc->wred[warp][0] = s1;
+            sc->wred[warp][1] = s2;
+            if (warp == 0) sc->cand_n = 0;
         }
-        __syncthreads();
-        if (warp == 0) {
-            s = lane < NW ? sc->wred[lane][0] : 0.0;
-            ss = lane < NW ? sc->wred[lane][1] : 0.0;
-            s = warp_sum_d(s);
-            ss = warp_sum_d(ss);
-            if (lane == 0) {
-                p.row_stats[2 * row] = s;
-                p.row_stats[2 * row + 1] = ss;
+        __syncthreads();  // CTA-wide: also tells the run-ahead warps that the partials have been read
+        s1 = lane < (n_group >> 5) ? sc->wred[lane][0] : 0.0;
+        s2 = lane < (n_group >> 5) ? sc->wred[lane][1] : 0.0;
+        s1 = warp_sum_d(s1);
+        s2 = warp_sum_d(s2);
+
+        const double m = block_median<VPT>(v, p.K, s1, s2, sc, lane, warp, n_group);
+
+#pragma unroll
+        for (int tt = 0; tt < TPT; ++tt) {
+            if (p.out_f64) {
+                double* o = reinterpret_cast<double*>(p.out) + row * p.ldo + col0[tt];
+#pragma unroll
+                for (int i = 0; i < LOUT; ++i)
+                    if (i < nv[tt]) o[i] = v[tt * LOUT + i] - m;
+            } else {
+                float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0[tt];
+#pragma unroll
+                for (int i = 0; i < LOUT; ++i)
+                    if (i < nv[tt]) o[i] = (float)(v[tt * LOUT + i] - m);
             }
         }
-        // the next row's first barrier (after its gathers) orders the reuse of `sc`
+        if (tid == 0) {
+            // sum(v - m) and sum((v - m)^2) from the raw moments
+            p.row_stats[2 * row] = s1 - Kd * m;
+            p.row_stats[2 * row + 1] = fma(Kd * m, m, fma(-2.0 * m, s1, s2));
+        }
+        // the next row's barriers order the reuse of `sc`
     }
 }
 
@@ -654,9 +652,9 @@ static int occ_one(size_t smem, int* out) {
             if (c64) return bounded ? FN<2, 0, 0, true, true, 1>(__VA_ARGS__) : FN<2, 0, 0, false, true, 1>(__VA_ARGS__); \
             return bounded ? FN<2, 0, 0, true, false, 1>(__VA_ARGS__) : FN<2, 0, 0, false, false, 1>(__VA_ARGS__); \
         }                                                                                                  \
-        if (tier == 2 && tpt == 8) {                                                                       \
-            if (c64) return bounded ? FN<2, 0, 0, true, true, 8>(__VA_ARGS__) : FN<2, 0, 0, false, true, 8>(__VA_ARGS__); \
-            return bounded ? FN<2, 0, 0, true, false, 8>(__VA_ARGS__) : FN<2, 0, 0, false, false, 8>(__VA_ARGS__); \
+        if (tier == 2 && tpt == 4) {                                                                       \
+            if (c64) return bounded ? FN<2, 0, 0, true, true, 4>(__VA_ARGS__) : FN<2, 0, 0, false, true, 4>(__VA_ARGS__); \
+            return bounded ? FN<2, 0, 0, true, false, 4>(__VA_ARGS__) : FN<2, 0, 0, false, false, 4>(__VA_ARGS__); \
         }                                                                                                  \
     } while (0)
 
