@@ -93,10 +93,14 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
  * Steps 1-4 of tl/_infercnv.py:411-442 for n_rows cells: centre, clip to
  * +-lfc_clip, per-chromosome pyramid running mean decimated by `step`
  * (:179-244, :301-356), subtract the row median.
- *   out        [n_rows, ldo] float32 (out_is_f64 == 0) or float64
- *   row_stats  [n_rows, 2] float64: sum and sum of squares of the row of `out`
+ *   out        INTERMEDIATE [n_rows, ldo] float32 (out_is_f64 == 0) or float64,
+ *              ldo >= icnv_plan_tmp_width().  Its columns are in the kernel's
+ *              warp-tile order (so that every store is a full 128-byte line);
+ *              icnv_apply_threshold turns it into the natural [n_rows, K] matrix.
+ *   row_stats  [n_rows, 2] float64: sum and sum of squares of the row
  *              (inputs of the per-chunk std of :450)
  */
+int icnv_plan_tmp_width(const icnv_plan* plan, int64_t* ld_tmp);
 int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip,
                           void* out, int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream);
 int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* indices, const float* data,
@@ -109,11 +113,14 @@ int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* i
  * chunk_rows) entries. */
 int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int64_t chunk_rows, double dyn_thr,
                          double* thr, void* stream);
-/* Zero |v| < thr[chunk of row] in place; also emits per row sum|v| and the
- * number of non-zeros (inputs of cnv_score, tl/_scores.py:66, and of the CSR
- * conversion, tl/_infercnv.py:455).  thr == NULL: no zeroing, statistics only. */
-int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
-                         const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream);
+/* tmp (intermediate of icnv_smooth_*) -> out [n_rows, ldo >= K] in natural column
+ * order with |v| < thr[chunk of row] zeroed (strict, :451); also emits per row
+ * sum|v| and the number of non-zeros (inputs of cnv_score, tl/_scores.py:66, and
+ * of the CSR conversion, tl/_infercnv.py:455).  thr == NULL: no zeroing (the
+ * pre-threshold matrix, dynamic_threshold=None). */
+int icnv_apply_threshold(icnv_plan* plan, const void* tmp, int32_t is_f64, int64_t n_rows, int64_t ld_tmp,
+                         int64_t chunk_rows, const double* thr, void* out, int64_t ldo, double* row_abs_sum,
+                         int32_t* row_nnz, void* stream);
 
 /* Dense [n_rows, K] -> CSR (tl/_infercnv.py:455).  indptr [n_rows+1] int64 must
  * already hold the exclusive prefix sum of row_nnz; indices int32; data float32
@@ -137,6 +144,10 @@ int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_
  * and the ncu notes): CTAs per SM, threads, dynamic shared memory bytes. */
 int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* threads, int32_t* smem_bytes,
                           int32_t* n_sm);
+
+/* Developer aid (tools/timeline.py): when dev_buf != NULL the smoothing kernel writes clock64 stamps
+ * [grid][rows_per_cta][16] for the first rows_per_cta rows of every CTA.  NULL switches it off. */
+int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta);
 
 #ifdef __cplusplus
 }

@@ -51,16 +51,21 @@ def _stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), out: Path | None = None) -> Path:
+    """``defines`` / ``out`` build an experimental variant next to the product library (A/B timing
+    on one box through ICNV_LIB_PATH, see tools/ab.sh); the default call builds ``libicnv.so``."""
+    global LIB
+    if out is None and not force and not _stale():
         return LIB
     nvcc = _nvcc()
     OBJ_DIR.mkdir(exist_ok=True)
     logs = {}
+    tag = "" if out is None else "_" + Path(out).stem
+    target = LIB if out is None else Path(out)
 
     def compile_one(src: Path):
-        obj = OBJ_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        obj = OBJ_DIR / (src.stem + tag + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src.name] = r.stderr
         if r.returncode != 0:
@@ -69,16 +74,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(4, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources()))
-    tmp = LIB.with_suffix(".so.tmp")
+    tmp = target.with_suffix(".so.tmp")
     cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
-    tmp.replace(LIB)
-    (OBJ_DIR / "ptxas.log").write_text("\n".join(f"==== {k}\n{v}" for k, v in logs.items()))
+    tmp.replace(target)
+    (OBJ_DIR / f"ptxas{tag}.log").write_text("\n".join(f"==== {k}\n{v}" for k, v in logs.items()))
     if verbose:
-        print(f"built {LIB} ({LIB.stat().st_size / 1e6:.1f} MB)")
-    return LIB
+        print(f"built {target} ({target.stat().st_size / 1e6:.1f} MB)")
+    return target
 
 
 if __name__ == "__main__":

@@ -134,42 +134,55 @@ class DevicePlan:
         self._ref_keepalive = ref
 
     # -- smoothing --------------------------------------------------------------------------------
-    def smooth(self, X, lfc_clip: float, out=None, row_stats=None, out_dtype=None):
-        """Steps 1-4 for the rows of ``X`` -> ``(out [n, K], row_stats [n, 2])``."""
+    def tmp_width(self) -> int:
+        w = C.c_int64()
+        _lib.check(self.lib.icnv_plan_tmp_width(self.handle, C.byref(w)), "icnv_plan_tmp_width")
+        return int(w.value)
+
+    def smooth(self, X, lfc_clip: float, tmp=None, row_stats=None, out_dtype=None):
+        """Steps 1-4 for the rows of ``X`` -> ``(tmp [n, tmp_width], row_stats [n, 2])``.
+
+        ``tmp`` is the kernel's intermediate in warp-tile column order; ``threshold`` turns it into
+        the natural ``[n, K]`` matrix (with or without the noise filter)."""
         torch = _torch()
         out_dtype = out_dtype or torch.float32
         if isinstance(X, tuple):
             n = X[0].numel() - 1
         else:
             n = X.shape[0]
-        if out is None:
-            out = torch.empty((n, self.K), dtype=out_dtype, device=self.device)
+        if tmp is None:
+            tmp = torch.empty((n, self.tmp_width()), dtype=out_dtype, device=self.device)
         if row_stats is None:
             row_stats = torch.empty((n, 2), dtype=torch.float64, device=self.device)
-        is64 = int(out.dtype == torch.float64)
+        is64 = int(tmp.dtype == torch.float64)
+        ld = tmp.stride(0) if n else self.tmp_width()
         if isinstance(X, tuple):
             indptr, indices, data = X
             rc = self.lib.icnv_smooth_csr_f32(
-                self.handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), n, float(lfc_clip), _lib.ptr(out), is64,
-                out.stride(0) if n else self.K, _lib.ptr(row_stats), self._stream(),
+                self.handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), n, float(lfc_clip), _lib.ptr(tmp), is64,
+                ld, _lib.ptr(row_stats), self._stream(),
             )
         else:
             assert X.dtype == torch.float32 and X.stride(1) == 1
             rc = self.lib.icnv_smooth_dense_f32(
-                self.handle, _lib.ptr(X), n, X.stride(0), float(lfc_clip), _lib.ptr(out), is64,
-                out.stride(0) if n else self.K, _lib.ptr(row_stats), self._stream(),
+                self.handle, _lib.ptr(X), n, X.stride(0), float(lfc_clip), _lib.ptr(tmp), is64, ld, _lib.ptr(row_stats),
+                self._stream(),
             )
         _lib.check(rc, "icnv_smooth")
-        return out, row_stats
+        return tmp, row_stats
 
-    def threshold(self, out, row_stats, chunk_rows: int, dynamic_threshold):
-        """Step 5 in place; returns ``(thr or None, row_abs_sum, row_nnz)``."""
+    def threshold(self, tmp, row_stats, chunk_rows: int, dynamic_threshold, out=None):
+        """Step 5: ``tmp`` -> natural-order ``out [n, K]`` with the per-chunk noise filter applied
+        (``dynamic_threshold=None``: no filter).  Returns ``(out, thr or None, row_abs_sum, row_nnz)``."""
         torch = _torch()
-        n, K = out.shape
+        n = tmp.shape[0]
+        K = self.K
+        if out is None:
+            out = torch.empty((n, K), dtype=tmp.dtype, device=self.device)
         row_abs = torch.empty((n,), dtype=torch.float64, device=self.device)
         row_nnz = torch.empty((n,), dtype=torch.int32, device=self.device)
         thr = None
-        is64 = int(out.dtype == torch.float64)
+        is64 = int(tmp.dtype == torch.float64)
         if dynamic_threshold is not None and n > 0:
             n_chunks = math.ceil(n / chunk_rows)
             thr = torch.empty((n_chunks,), dtype=torch.float64, device=self.device)
@@ -180,11 +193,12 @@ class DevicePlan:
         if n > 0:
             _lib.check(
                 self.lib.icnv_apply_threshold(
-                    _lib.ptr(out), is64, n, K, out.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(row_abs), _lib.ptr(row_nnz), self._stream()
+                    self.handle, _lib.ptr(tmp), is64, n, tmp.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(out), out.stride(0),
+                    _lib.ptr(row_abs), _lib.ptr(row_nnz), self._stream(),
                 ),
                 "icnv_apply_threshold",
             )
-        return thr, row_abs, row_nnz
+        return out, thr, row_abs, row_nnz
 
     def to_csr(self, out, row_nnz):
         """Dense thresholded block -> device CSR ``(indptr int64, indices int32, data)``."""

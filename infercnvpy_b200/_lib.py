@@ -34,10 +34,12 @@ SIGNATURES = {
     "icnv_smooth_dense_f32": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_smooth_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_chunk_threshold": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_vp, c_vp]),
-    "icnv_apply_threshold": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
+    "icnv_apply_threshold": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "icnv_plan_tmp_width": (C.c_int, [c_vp, c_i64p]),
     "icnv_dense_to_csr": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_rowabs_csr": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_rowabs_dense": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "icnv_debug_set_timeline": (C.c_int, [c_vp, C.c_int]),
     "icnv_label_sums": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int32, c_vp, c_vp, c_vp]),
 }
 
@@ -55,12 +57,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not _LIB_PATH.exists():
+    import os
+
+    path = Path(os.environ.get("ICNV_LIB_PATH", _LIB_PATH))  # developer A/B builds only
+    if not path.exists():
         raise IcnvError(
-            f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). infercnvpy_b200 has no CPU fallback."
         )
-    lib = C.CDLL(str(_LIB_PATH))
+    lib = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res

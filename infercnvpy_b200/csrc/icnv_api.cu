@@ -24,7 +24,8 @@ int aux_mean_from_sums(const double*, const int64_t*, int, int, void*, bool, cud
 int aux_nnz_to_indptr(const int32_t*, int64_t, int64_t*, cudaStream_t);
 int aux_build_bounds(const void*, bool, int, int, const int32_t*, int64_t, void*, void*, bool, cudaStream_t);
 int aux_chunk_threshold(const double*, int64_t, int64_t, int64_t, double, double*, cudaStream_t);
-int aux_apply_threshold(void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
+int aux_finalize(const void*, bool, int64_t, int64_t, const Task*, int, int64_t, const double*, void*, int64_t, double*, int32_t*, cudaStream_t);
+int smooth_raw_base(uint32_t* base);
 int aux_dense_to_csr(const void*, bool, int64_t, int64_t, int64_t, const int64_t*, int32_t*, void*, cudaStream_t);
 int aux_rowabs_csr(const int64_t*, const void*, bool, int64_t, double*, cudaStream_t);
 int aux_rowabs_dense(const void*, bool, int64_t, int64_t, int64_t, double*, cudaStream_t);
@@ -72,9 +73,11 @@ struct icnv_plan {
     bool group_ok = false;
     int base_tier = 2;
     int32_t gs = 0, NG = 0, NGpad = 0, NQ = 0, qstar = -1, Gpad = 0;
+    uint32_t raw_base = 0;
     int32_t n_tasks_g = 0;
     DevBuf<uint32_t> off_w;  // [warp-block][j][lane][u] byte offsets into the staged row
     DevBuf<int32_t> cols_w;  // same layout, column index, pad = -1 (input of the bounds kernel)
+    DevBuf<int32_t> grp_w;   // [warp-block][lane][u] group whose partial sums this slot produces
     DevBuf<float> lo_w, hi_w;
     DevBuf<double> alpha, beta, cw;
     DevBuf<Task> tasks_g;
@@ -97,6 +100,7 @@ struct icnv_plan {
     ~icnv_plan() {
         off_w.release();
         cols_w.release();
+        grp_w.release();
         lo_w.release();
         hi_w.release();
         alpha.release();
@@ -259,32 +263,95 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         p->NGpad = (p->NG + 3) / 4 * 4;
         if (p->NGpad == 0) p->NGpad = 4;
         p->Gpad = (n_genes + 1 + 3) / 4 * 4;
-        // tables in kernel order: entry ((wb*gs + j)*32 + lane)*4 + u  <->  element j of group u*nquads + wb*32 + lane
+        // ---- assign groups to (warp-block, u, lane) slots.
+        // A warp-level gather LDS for (wb, u, j) reads element j of the 32 groups in that slot set; its cost
+        // is the largest number of distinct addresses that fall into one shared-memory bank.  Genes are not
+        // position-sorted in memory, so with groups laid out in natural order that is ~3.5 wavefronts per
+        // LDS.  A constructive greedy (take, for every lane slot, the unassigned group that adds the fewest
+        // bank collisions over all j) brings it to ~2.0.  Lane l only takes groups with g % 8 == l % 8 so
+        // the 16-byte partial-sum stores AB[g] of a quarter-warp hit 8 different bank groups.
         const int nquads = p->NGpad / 4;
         const int n_wb = (nquads + 31) / 32;
-        std::vector<int32_t> seg_of_group(p->NG);
-        for (int c = 0; c < n_seg; ++c)
-            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g) seg_of_group[g] = c;
-        const size_t n_entries = (size_t)n_wb * gs * 32 * 4;
-        std::vector<uint32_t> off(n_entries, (uint32_t)n_genes * 4u);
-        std::vector<int32_t> cols(n_entries, -1);
-        for (int wb = 0; wb < n_wb; ++wb)
-            for (int j = 0; j < gs; ++j)
-                for (int lane = 0; lane < 32; ++lane)
-                    for (int u = 0; u < 4; ++u) {
-                        const int quad = wb * 32 + lane;
-                        if (quad >= nquads) continue;
-                        const int32_t g = u * nquads + quad;
-                        if (g >= p->NG) continue;
-                        const int c = seg_of_group[g];
-                        const int32_t s0 = p->seg_off[c];
-                        const int32_t Gc = p->seg_off[c + 1] - s0;
-                        const int32_t pos = (g - gbase[c]) * gs + j;
-                        if (pos >= Gc) continue;
-                        const size_t e = (((size_t)wb * gs + j) * 32 + lane) * 4 + u;
-                        off[e] = (uint32_t)p->gene_idx[s0 + pos] * 4u;
-                        cols[e] = p->gene_idx[s0 + pos];
+        const int nsets = n_wb * 4;
+        std::vector<int32_t> gcol((size_t)p->NG * gs, -1);  // column of element j of group g, -1 = pad
+        for (int c = 0; c < n_seg; ++c) {
+            const int32_t s0 = p->seg_off[c];
+            const int32_t Gc = p->seg_off[c + 1] - s0;
+            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g)
+                for (int j = 0; j < gs; ++j) {
+                    const int32_t pos = (g - gbase[c]) * gs + j;
+                    if (pos < Gc) gcol[(size_t)g * gs + j] = p->gene_idx[s0 + pos];
+                }
+        }
+        auto bank_of = [&](int32_t g, int j) {
+            const int32_t col = gcol[(size_t)g * gs + j];
+            return (col < 0 ? n_genes : col) & 31;
+        };
+        std::vector<int32_t> slot_group((size_t)nsets * 32, -1);
+        {
+            std::vector<std::vector<int32_t>> pool(8);
+            for (int32_t g = 0; g < p->NG; ++g) pool[g & 7].push_back(g);
+            std::vector<int> cnt((size_t)gs * 32), mx(gs);
+            for (int sidx = 0; sidx < nsets; ++sidx) {
+                std::fill(cnt.begin(), cnt.end(), 0);
+                std::fill(mx.begin(), mx.end(), 0);
+                for (int lane = 0; lane < 32; ++lane) {
+                    auto& cand = pool[lane & 7];
+                    if (cand.empty()) continue;
+                    long best_score = -1;
+                    size_t best_k = 0;
+                    for (size_t k = 0; k < cand.size(); ++k) {
+                        long add = 0, load = 0;
+                        for (int j = 0; j < gs; ++j) {
+                            const int nc = cnt[(size_t)j * 32 + bank_of(cand[k], j)] + 1;
+                            add += nc > mx[j] ? nc - mx[j] : 0;
+                            load += nc;
+                        }
+                        const long score = add * 4096 + load;
+                        if (best_score < 0 || score < best_score) {
+                            best_score = score;
+                            best_k = k;
+                        }
                     }
+                    const int32_t g = cand[best_k];
+                    cand[best_k] = cand.back();
+                    cand.pop_back();
+                    slot_group[(size_t)sidx * 32 + lane] = g;
+                    for (int j = 0; j < gs; ++j) {
+                        int& c2 = cnt[(size_t)j * 32 + bank_of(g, j)];
+                        c2 += 1;
+                        if (c2 > mx[j]) mx[j] = c2;
+                    }
+                }
+            }
+            for (int c8 = 0; c8 < 8; ++c8)
+                if (!pool[c8].empty()) {
+                    set_error("internal: group slots exhausted");
+                    return ICNV_EINVAL;
+                }
+        }
+        // tables in kernel order: entry ((wb*gs + j)*32 + lane)*4 + u  <->  element j of the group in slot (wb, u, lane)
+        const size_t n_entries = (size_t)n_wb * gs * 32 * 4;
+        uint32_t raw_base = 0;
+        if (smooth_raw_base(&raw_base)) return ICNV_ECUDA;
+        p->raw_base = raw_base;
+        std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
+        std::vector<int32_t> cols(n_entries, -1);
+        std::vector<int32_t> grp((size_t)n_wb * 32 * 4, p->NGpad);  // empty slots store their zeros to a pad group
+        for (int wb = 0; wb < n_wb; ++wb)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int u = 0; u < 4; ++u) {
+                    const int32_t g = slot_group[((size_t)wb * 4 + u) * 32 + lane];
+                    if (g < 0) continue;
+                    grp[((size_t)wb * 32 + lane) * 4 + u] = g;
+                    for (int j = 0; j < gs; ++j) {
+                        const int32_t col = gcol[(size_t)g * gs + j];
+                        if (col < 0) continue;
+                        const size_t e = (((size_t)wb * gs + j) * 32 + lane) * 4 + u;
+                        off[e] = raw_base + (uint32_t)col * 4u;
+                        cols[e] = col;
+                    }
+                }
         // weights: within a group the pyramid is linear in j except (at most) the group holding the peak
         std::vector<double> alpha(p->NQ, 0.0), beta(p->NQ, 0.0), cw(gs, 0.0);
         p->qstar = -1;
@@ -318,7 +385,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             }
         }
         p->n_tasks_g = (int32_t)tasks.size();
-        if (p->off_w.upload(off) || p->cols_w.upload(cols) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
+        if (p->off_w.upload(off) || p->cols_w.upload(cols) || p->grp_w.upload(grp) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
             p->cw.upload(cw) || p->tasks_g.upload(tasks))
             return ICNV_ECUDA;
         if (p->lo_w.alloc(n_entries) || p->hi_w.alloc(n_entries)) return ICNV_ECUDA;
@@ -343,6 +410,15 @@ int icnv_plan_out_width(const icnv_plan* plan, int64_t* K) {
 int icnv_plan_out_offsets(const icnv_plan* plan, int64_t* out_off_host) {
     if (!plan || !out_off_host) return ICNV_EINVAL;
     std::copy(plan->out_off.begin(), plan->out_off.end(), out_off_host);
+    return ICNV_OK;
+}
+int icnv_plan_tmp_width(const icnv_plan* plan, int64_t* ld_tmp) {
+    if (!plan || !ld_tmp) return ICNV_EINVAL;
+    Choice ch;
+    int rc = choose(*plan, plan->c64, &ch);
+    if (rc) return rc;
+    const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+    *ld_tmp = (int64_t)((n_tasks + 31) / 32) * 32 * LOUT;
     return ICNV_OK;
 }
 int icnv_plan_kernel_tier(const icnv_plan* plan) {
@@ -425,13 +501,21 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
     return ICNV_OK;
 }
 
+static long long* g_dbg_ptr = nullptr;
+static int g_dbg_rows = 0;
+extern "C" int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta) {
+    g_dbg_ptr = dev_buf;
+    g_dbg_rows = rows_per_cta;
+    return ICNV_OK;
+}
+
 static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo,
                          double* row_stats, void* stream) {
     if (!plan->have_ref) {
         set_error("smooth: icnv_plan_set_reference has not been called");
         return ICNV_EINVAL;
     }
-    if (!out || !row_stats || ldo < plan->K || !(lfc_clip >= 0)) {
+    if (!out || !row_stats || !(lfc_clip >= 0)) {
         set_error("smooth: bad argument");
         return ICNV_EINVAL;
     }
@@ -439,6 +523,13 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     Choice ch;
     int rc = choose(*plan, plan->c64, &ch);
     if (rc) return rc;
+    {
+        const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+        if (ldo < (int64_t)((n_tasks + 31) / 32) * 32 * LOUT) {
+            set_error("smooth: intermediate pitch smaller than icnv_plan_tmp_width");
+            return ICNV_EINVAL;
+        }
+    }
     if (ch.tier == 2 && !sp.X) {
         set_error("smooth: CSR input is only fused into the grouped kernels; densify first for this (window, step)");
         return ICNV_EUNSUPPORTED;
@@ -451,6 +542,8 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     sp.NQ = plan->NQ;
     sp.qstar = plan->qstar;
     sp.off_w = plan->off_w.ptr;
+    sp.raw_base = plan->raw_base;
+    sp.grp_w = plan->grp_w.ptr;
     sp.lo_w = plan->lo_w.ptr;
     sp.hi_w = plan->hi_w.ptr;
     sp.alpha = plan->alpha.ptr;
@@ -474,6 +567,8 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     sp.ldo = ldo;
     sp.out_f64 = out_is_f64;
     sp.row_stats = row_stats;
+    sp.dbg = g_dbg_ptr;
+    sp.dbg_rows = g_dbg_rows;
     sp.use_tma = sp.X && (sp.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp.X) & 15) == 0) && (plan->G % 4 == 0);
     int occ = 0;
     rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.smem, &occ);
@@ -524,13 +619,19 @@ int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int
     return aux_chunk_threshold(row_stats, n_rows, K, chunk_rows, dyn_thr, thr, (cudaStream_t)stream);
 }
 
-int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
-                         const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream) {
-    if (!out || chunk_rows < 1 || ldo < K) {
+int icnv_apply_threshold(icnv_plan* plan, const void* tmp, int32_t is_f64, int64_t n_rows, int64_t ld_tmp, int64_t chunk_rows,
+                         const double* thr, void* out, int64_t ldo, double* row_abs_sum, int32_t* row_nnz, void* stream) {
+    if (!plan || !tmp || !out || chunk_rows < 1 || ldo < plan->K) {
         set_error("icnv_apply_threshold: bad argument");
         return ICNV_EINVAL;
     }
-    return aux_apply_threshold(out, out_is_f64 != 0, n_rows, K, ldo, chunk_rows, thr, row_abs_sum, row_nnz, (cudaStream_t)stream);
+    Choice ch;
+    int rc = choose(*plan, plan->c64, &ch);
+    if (rc) return rc;
+    const Task* tasks = ch.tier < 2 ? plan->tasks_g.ptr : plan->tasks_d.ptr;
+    const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+    return aux_finalize(tmp, is_f64 != 0, n_rows, ld_tmp, tasks, n_tasks, chunk_rows, thr, out, ldo, row_abs_sum, row_nnz,
+                        (cudaStream_t)stream);
 }
 
 int icnv_dense_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, const int64_t* indptr,

@@ -207,28 +207,53 @@ __global__ void __launch_bounds__(256) chunk_threshold_kernel(const double* __re
     }
 }
 
-// Zero |v| < thr (strict, :451), per-row sum|v| and nnz.  One warp per row, lanes along the row.
+// Step 5 proper: read the smoothing kernel's intermediate (warp-tile order, see SmoothParams::out), zero
+// |v| < thr (strict, :451), write the matrix in natural column order and emit per-row sum|v| and nnz.
+// One warp per row; a tile's 32 tasks cover one contiguous column range, so the un-permute goes through a
+// 32*LOUT-value staging slab per warp and both the read and the write are fully coalesced.
 template <typename T>
-__global__ void __launch_bounds__(256) apply_threshold_kernel(T* __restrict__ out, int64_t n_rows, int64_t K, int64_t ldo,
-                                                              int64_t chunk_rows, const double* __restrict__ thr,
-                                                              double* __restrict__ row_abs, int32_t* __restrict__ row_nnz) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) finalize_kernel(const T* __restrict__ tmp, int64_t n_rows, int64_t ld_tmp,
+                                                       const Task* __restrict__ tasks, int n_tasks, int64_t chunk_rows,
+                                                       const double* __restrict__ thr, T* __restrict__ out, int64_t ldo,
+                                                       double* __restrict__ row_abs, int32_t* __restrict__ row_nnz) {
+    __shared__ T stage[8][32 * LOUT];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int n_tiles = (n_tasks + 31) >> 5;
     for (int64_t r = warp; r < n_rows; r += n_warps) {
         const double t = thr ? thr[r / chunk_rows] : -1.0;
-        T* row = out + r * ldo;
         double a = 0.0;
         int nz = 0;
-        for (int64_t c = lane; c < K; c += 32) {
-            const T v = row[c];
-            const double av = fabs((double)v);
-            if (av < t) {
-                row[c] = (T)0;
-            } else if (av != 0.0) {  // also counts NaN like scipy's != 0 would
-                a += av;
-                nz += 1;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            const int ti = tile * 32 + lane;
+            int col0 = 0, cnt = 0;
+            if (ti < n_tasks) {
+                const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks) + ti);
+                col0 = tk.y;
+                cnt = (tk.w & 0xFF) ? 1 : tk.z;
             }
+            const int base = __shfl_sync(0xffffffffu, col0, 0);
+            const int end = __reduce_max_sync(0xffffffffu, col0 + cnt);
+            const T* src = tmp + r * ld_tmp + (int64_t)tile * (32 * LOUT) + lane;
+#pragma unroll
+            for (int i = 0; i < LOUT; ++i) {
+                T x = src[i * 32];
+                if (i < cnt) {
+                    const double av = fabs((double)x);
+                    if (av < t) {
+                        x = (T)0;
+                    } else if (av != 0.0) {
+                        a += av;
+                        nz += 1;
+                    }
+                    stage[wib][col0 - base + i] = x;
+                }
+            }
+            __syncwarp();
+            T* dst = out + r * ldo + base;
+            for (int k = lane; k < end - base; k += 32) dst[k] = stage[wib][k];
+            __syncwarp();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -408,13 +433,15 @@ int aux_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int6
     return 0;
 }
 
-int aux_apply_threshold(void* out, bool f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows, const double* thr,
-                        double* row_abs, int32_t* row_nnz, cudaStream_t st) {
+int aux_finalize(const void* tmp, bool f64, int64_t n_rows, int64_t ld_tmp, const Task* tasks, int n_tasks, int64_t chunk_rows,
+                 const double* thr, void* out, int64_t ldo, double* row_abs, int32_t* row_nnz, cudaStream_t st) {
     if (n_rows == 0) return 0;
     if (f64)
-        apply_threshold_kernel<double><<<grid_for_rows(n_rows), 256, 0, st>>>((double*)out, n_rows, K, ldo, chunk_rows, thr, row_abs, row_nnz);
+        finalize_kernel<double><<<grid_for_rows(n_rows), 256, 0, st>>>((const double*)tmp, n_rows, ld_tmp, tasks, n_tasks, chunk_rows, thr,
+                                                                      (double*)out, ldo, row_abs, row_nnz);
     else
-        apply_threshold_kernel<float><<<grid_for_rows(n_rows), 256, 0, st>>>((float*)out, n_rows, K, ldo, chunk_rows, thr, row_abs, row_nnz);
+        finalize_kernel<float><<<grid_for_rows(n_rows), 256, 0, st>>>((const float*)tmp, n_rows, ld_tmp, tasks, n_tasks, chunk_rows, thr,
+                                                                     (float*)out, ldo, row_abs, row_nnz);
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }

@@ -45,8 +45,11 @@ struct SmoothParams {
     int32_t NQ;       // groups per window
     int32_t qstar;    // group-in-window holding the pyramid peak (non-linear weights), -1 if none
     // Per-gene tables in the order the kernel walks them: [warp-block of 32 quads][j < gs][lane][u < 4];
-    // entry (wb, j, lane, u) belongs to element j of group u*(NGpad/4) + wb*32 + lane.
-    const uint32_t* off_w;  // BYTE offset of the gene inside the staged raw row (4*G = zero pad slot)
+    // entry (wb, j, lane, u) belongs to element j of group grp_w[(wb*32 + lane)*4 + u] (host-optimised
+    // assignment that minimises shared-memory bank collisions of the gathers).
+    const int32_t* grp_w;   // [warp-block][lane][u] group index (NGpad = unused slot)
+    const uint32_t* off_w;  // shared-window BYTE address of the gene inside the staged raw row (zero pad slot = gene G)
+    uint32_t raw_base;      // shared-window address of raw[0] baked into off_w (checked by the kernel)
     const float* lo_w;      // reference lower bound (== ref when one category)
     const float* hi_w;      // upper bound (only read when BOUNDED)
     const double* alpha;    // [NQ] weight of A_g = sum_j x
@@ -68,10 +71,15 @@ struct SmoothParams {
     const Task* tasks;
     int32_t n_tasks;
     int32_t K;
+    // intermediate [n_rows, ldo] in warp-tile order: value i of task t sits at (t/32)*32*LOUT + i*32 + t%32,
+    // so every store instruction of a warp writes 128 contiguous bytes; icnv_apply_threshold un-permutes
     void* out;
     int64_t ldo;
     int32_t out_f64;
     double* row_stats;
+    // optional developer timeline: [grid][dbg_rows][16] clock64 stamps (nullptr = off)
+    long long* dbg;
+    int32_t dbg_rows;
 };
 
 // ---------------------------------------------------------------- PTX helpers

@@ -27,19 +27,29 @@
 namespace icnv {
 
 struct __align__(16) Scratch {
-    uint4 wcnt[2][NW];
-    double wred[NW][2];
-    double cand[CAND_CAP];
-    double med[2];
+    uint4 wcnt[2][NW];      // generic 8-bin passes: per-warp packed counts (double-buffered by pass parity)
+    uint4 fcnt[NW];         // fast first pass: 16 one-byte counters per warp
+    int2 fmeta[NW];         // fast first pass: {below | in-region << 16, byte-overflow flag}
+    double wred[2][NW][2];  // per-warp exact (sum, sum of squares) of the row, by row parity
+    double wmm[NW][2];      // straddle path: per-warp max-below / min-above
+    double cand[CAND_CAP];  // final candidates (+inf padded)
+    double mrow[2];         // median of the row, by row parity (row statistics are finished one row later)
+    long long prow[2];      // row index belonging to mrow / wred
+    float2 wsumf[NW];       // per-warp fp32 (sum, sum of squares): steers the first bracket only
     unsigned long long mbar;
     int cand_n;
     int bcnt[NW];
     int btotal;
-    int next_wb[2];  // phase-2 work stealing: next warp-block of quads, per row parity
+    int next_wb[2];         // phase-2 work stealing: next warp-block of quads, per row parity
 };
 constexpr int SCRATCH_BYTES = (sizeof(Scratch) + 15) / 16 * 16;
 
 __device__ __forceinline__ double warp_sum_d(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_sum_f(float x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
@@ -83,31 +93,110 @@ __device__ __forceinline__ unsigned long long ordered_bits(double v) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-// Exact median of the K finite values spread over the CTA's registers (np.median semantics,
+// Exact median of the K finite values spread over the group's registers (np.median semantics,
 // /root/reference/src/infercnvpy/tl/_infercnv.py:442).  Unused slots hold +inf (they sort last and
-// never reach the middle ranks).  S1 / S2 = sum and sum of squares of the K values, known to every
-// thread; they only steer the first bracket — exactness never depends on them.  Returns the median to
-// every thread.  Must be called by exactly the first `nthreads` threads of the CTA (whole warps).
+// never reach the middle ranks).  `mean` / `var` (fp32 estimates of the K values) only steer the first
+// bracket — exactness never depends on them.  Returns the median to every thread.  Must be called by
+// exactly the first `nthreads` threads of the CTA (whole warps); sc->cand must be +inf, sc->cand_n 0.
+//
+// Keys: key(v) = saturating floor((v - (mean - h)) * 2^31 / h), h = 1.02 sigma: 32 bits, monotone in v; the
+// median always lies inside (|median - mean| <= sigma).  Pass 1 (one barrier) counts the 16 bins of width
+// h/32 around the mean plus everything below them; for near-symmetric rows that already isolates <= 32
+// candidates, which every warp then ranks exactly in fp64.  Anything else (median outside those bins,
+// a crowded bin, ties) continues with generic 8-bin passes and, ultimately, an exact bitwise select.
 template <int VPT>
-__device__ double block_median(const double (&v)[VPT], int K, double S1, double S2, Scratch* sc, int lane, int warp,
-                               int nthreads) {
+__device__ double block_median(const double (&v)[VPT], int K, float mean, float var, Scratch* sc, int lane, int warp,
+                               int nthreads, long long* dbg) {
+#define MED_STAMP(k)                                   \
+    do {                                               \
+        if (dbg != nullptr) dbg[(k)] = clock64();      \
+    } while (0)
     const int nwarps = nthreads >> 5;
-    // the median lies within one standard deviation of the mean; 2 % slack for the fp32 arithmetic
-    const float invK = 1.f / (float)K;
-    const float mean = (float)S1 * invK;
-    const float var = fmaxf((float)S2 * invK - mean * mean, 0.f);
     const float half = fmaxf(1.02f * sqrtf(var) + 1e-6f * fabsf(mean), 1e-20f);
     const double kbase = (double)(mean - half);
     const double kscale = (double)(2147483648.f / half);
-    // key(v) = saturating floor((v - kbase) * kscale): monotone in v, 32 bits; +inf -> 0xFFFFFFFF
     uint32_t key[VPT];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) key[i] = __double2uint_rd((v[i] - kbase) * kscale);
 
+    MED_STAMP(8);
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
     uint32_t klo = 0, ksplit = 0;
-    int shift = 29, below = 0, state = 0, buf = 0;
-    while (true) {
+    int shift = 29, below = 0, state = -1, buf = 0;
+
+#ifdef ICNV_FASTPASS  // measured slower on B200 (tools/ab.py, gpurun_out/ab1.log): off by default
+    if constexpr (VPT == LOUT) {
+        // ---- pass 1: 16 fine bins t = (key >> 26) - 24 in [0, 16), i.e. mean +- h/4
+        uint32_t cA = 0, cB = 0;  // 4-bit counters for t = 0..7 and 8..15
+        int nb = 0, nreg = 0;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+            const int t = (int)(key[i] >> 26) - 24;
+            const bool in = (unsigned)t < 16u;
+            const uint32_t inc = 1u << ((t & 7) << 2);
+            cA += (in && t < 8) ? inc : 0u;
+            cB += (in && t >= 8) ? inc : 0u;
+            nb += t < 0;
+            nreg += in;
+        }
+        // bytes: a0 = t 0,2,4,6; a1 = t 1,3,5,7; b0 = t 8,10,12,14; b1 = t 9,11,13,15
+        uint32_t a0 = cA & 0x0F0F0F0Fu, a1 = (cA >> 4) & 0x0F0F0F0Fu, b0 = cB & 0x0F0F0F0Fu, b1w = (cB >> 4) & 0x0F0F0F0Fu;
+        a0 = __reduce_add_sync(0xffffffffu, a0);
+        a1 = __reduce_add_sync(0xffffffffu, a1);
+        b0 = __reduce_add_sync(0xffffffffu, b0);
+        b1w = __reduce_add_sync(0xffffffffu, b1w);
+        const int meta = __reduce_add_sync(0xffffffffu, nb | (nreg << 16));
+        if (lane == 0) {
+            // a byte counter wraps if > 255 values of this warp share one bin (ties): detected by the byte sum
+            const int bytesum = __dp4a(a0, 0x01010101u, 0u) + __dp4a(a1, 0x01010101u, 0u) + __dp4a(b0, 0x01010101u, 0u) +
+                                __dp4a(b1w, 0x01010101u, 0u);
+            sc->fcnt[warp] = make_uint4(a0, a1, b0, b1w);
+            sc->fmeta[warp] = make_int2(meta, bytesum != (meta >> 16));
+        }
+        MED_STAMP(14);
+        group_sync(nthreads);
+        MED_STAMP(9);
+        // every warp derives the decision itself: lane t < 16 owns fine bin t
+        const int widx = ((lane >> 3) & 1) * 2 + (lane & 1), kb = ((lane & 7) >> 1) * 8;
+        int f = 0, nbt = 0, bad = 0;
+        for (int w = 0; w < nwarps; ++w) {
+            const uint32_t word = reinterpret_cast<const uint32_t*>(&sc->fcnt[w])[widx];
+            const int2 mt = sc->fmeta[w];
+            f += (word >> kb) & 0xFFu;
+            nbt += mt.x & 0xFFFF;
+            bad |= mt.y;
+        }
+        if (lane >= 16) f = 0;
+        int incl = f;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        incl += nbt;
+        const unsigned m1 = __ballot_sync(0xffffffffu, lane < 16 && incl > r1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, lane < 16 && incl > r2);
+        const int b1 = __ffs(m1) - 1, b2 = __ffs(m2) - 1;
+        if (!bad && r1 >= nbt && b1 >= 0 && b2 >= 0) {
+            if (b1 != b2) {
+                state = 2;
+                ksplit = (uint32_t)(24 + b2) << 26;
+            } else {
+                klo = (uint32_t)(24 + b1) << 26;
+                below = __shfl_sync(0xffffffffu, incl - f, b1);
+                const int n_in = __shfl_sync(0xffffffffu, f, b1);
+                if (n_in <= CAND_CAP) {
+                    state = 1;
+                    shift = 26;
+                } else {
+                    shift = 23;  // crowded bin: generic passes inside it
+                }
+            }
+        }
+    }
+#endif
+
+    while (state < 0) {
         uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;  // 16-bit fields: bins (0,1) (2,3) (4,5) (6,7)
 #pragma unroll
         for (int g0 = 0; g0 < VPT; g0 += LOUT) {
@@ -174,6 +263,7 @@ __device__ double block_median(const double (&v)[VPT], int K, double S1, double 
         shift = shift >= 3 ? shift - 3 : 0;
     }
 
+    MED_STAMP(10);
     double m;
     if (state == 1) {
         // <= CAND_CAP values share the final key range: rank them exactly in fp64
@@ -184,21 +274,21 @@ __device__ double block_median(const double (&v)[VPT], int K, double S1, double 
                 sc->cand[slot] = v[i];
             }
         group_sync(nthreads);
-        if (warp == 0) {
-            const int n = sc->cand_n;
-            const double mine = lane < n ? sc->cand[lane] : 0.0;
-            int rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const double o = sc->cand[j];
-                rank += (o < mine) || (o == mine && j < lane);
-            }
-            if (lane < n) {
-                if (rank == r1 - below) sc->med[0] = mine;
-                if (rank == r2 - below) sc->med[1] = mine;
-            }
+        MED_STAMP(11);
+        // every warp ranks the (+inf padded) candidate list itself: lane i owns candidate i
+        const int n = sc->cand_n;
+        const double mine = sc->cand[lane];
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < CAND_CAP; ++j) {
+            const double o = sc->cand[j];
+            rank += (o < mine) || (o == mine && j < lane);
         }
-        group_sync(nthreads);
-        m = (sc->med[0] + sc->med[1]) / 2.0;
+        const unsigned q1 = __ballot_sync(0xffffffffu, lane < n && rank == r1 - below);
+        const unsigned q2 = __ballot_sync(0xffffffffu, lane < n && rank == r2 - below);
+        const double lo = __shfl_sync(0xffffffffu, mine, (__ffs(q1) - 1) & 31);
+        const double hi = __shfl_sync(0xffffffffu, mine, (__ffs(q2) - 1) & 31);
+        m = (lo + hi) / 2.0;
     } else if (state == 2) {
         // the two middle ranks sit on either side of a bin boundary
         double lo = -INFINITY, hi = INFINITY;
@@ -212,12 +302,12 @@ __device__ double block_median(const double (&v)[VPT], int K, double S1, double 
         lo = warp_max_d(lo);
         hi = warp_min_d(hi);
         if (lane == 0) {
-            sc->wred[warp][0] = lo;
-            sc->wred[warp][1] = hi;
+            sc->wmm[warp][0] = lo;
+            sc->wmm[warp][1] = hi;
         }
         group_sync(nthreads);
-        lo = lane < nwarps ? sc->wred[lane][0] : -INFINITY;
-        hi = lane < nwarps ? sc->wred[lane][1] : INFINITY;
+        lo = lane < nwarps ? sc->wmm[lane][0] : -INFINITY;
+        hi = lane < nwarps ? sc->wmm[lane][1] : INFINITY;
         lo = warp_max_d(lo);
         hi = warp_min_d(hi);
         m = (lo + hi) / 2.0;
@@ -252,17 +342,33 @@ __device__ double block_median(const double (&v)[VPT], int K, double S1, double 
         }
         m = (res[0] + res[1]) / 2.0;
     }
+    MED_STAMP(12);
+#undef MED_STAMP
     return m;
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT>
+#ifdef ICNV_AB_OCC1
+__global__ void __launch_bounds__(NT, 1) smooth_kernel(const SmoothParams p) {
+#else
 __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_kernel(const SmoothParams p) {
+#endif
     extern __shared__ __align__(16) unsigned char smem[];
     Scratch* sc = reinterpret_cast<Scratch*>(smem);
     unsigned char* carve = smem + SCRATCH_BYTES;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Logical warp numbering is reversed: the warps that own output values (the per-row critical path:
+    // windows, median, write-out) are the HIGHEST physical warp ids, which the warp scheduler favours;
+    // the run-ahead gather warps take the low ids.
+    const int lane = threadIdx.x & 31;
+#ifdef ICNV_AB_NOFLIP
+    const int warp = (int)(threadIdx.x >> 5);
+#else
+    const int warp = NW - 1 - (int)(threadIdx.x >> 5);
+#endif
+    const int tid = warp * 32 + lane;
+    constexpr int ISSUER = NT - 32;  // lane 0 of the last logical warp (a run-ahead warp) drives the TMA
     constexpr bool GROUPED = TIER < 2;
     constexpr int NQ_C = (TIER == 0) ? NWIN / GS : 0;
     constexpr bool M3_C = (TIER == 0) && ((NWIN / 2) % GS != 0);
@@ -309,7 +415,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     const bool dense = p.X != nullptr;
     if constexpr (GROUPED) {
         for (int i = p.G + tid; i < p.Gpad; i += NT) raw[i] = 0.f;
-        for (int i = p.NGpad + tid; i < p.NGpad + PAD_GROUPS; i += NT) {
+        for (int i = p.NG + tid; i < p.NGpad + PAD_GROUPS; i += NT) {
             AB[i] = make_double2(0.0, 0.0);
             if (Cp) Cp[i] = 0.0;
         }
@@ -331,6 +437,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
         sc->next_wb[0] = 0;
         sc->next_wb[1] = 0;
         sc->cand_n = 0;
+        if (GROUPED && (smem_u32(raw) & 0xFFFFFFu) != p.raw_base) __trap();  // host baked a different base
     }
     __syncthreads();
 
@@ -347,26 +454,52 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
 
     int64_t row = blockIdx.x;
     const bool tma = GROUPED && dense && p.use_tma;
-    if (tma && tid == 0 && row < p.n_rows) issue_row(row);
+    if (tma && tid == ISSUER && row < p.n_rows) issue_row(row);
 
     const float clipf = p.clipf;
     const int nquads = p.NGpad >> 2;
     const int n_wb = (nquads + 31) >> 5;
     const double Kd = (double)p.K;
-    const uint32_t raw_s = GROUPED ? smem_u32(raw) : 0u;
     // Only the warps that own output values ("group") take part in phase 3 / median / write-out; the others
     // go straight to the next row and work ahead on its gathers (barrier 1 = group only, barrier 0 = CTA).
     const int n_group = min(NT, ((p.n_tasks + 31) >> 5) << 5);
     const bool in_group = tid < n_group;
+    // task descriptors are row-invariant: fetch them once
+    int4 task[TPT];
+#pragma unroll
+    for (int tt = 0; tt < TPT; ++tt) {
+        const int ti = tid + tt * NT;
+        task[tt] = ti < p.n_tasks ? __ldg(reinterpret_cast<const int4*>(p.tasks) + ti) : make_int4(0, 0, 0, 0);
+    }
+    // sum(v - m) and sum((v - m)^2) of a finished row from its raw moments (thread 0, one row late)
+    auto finish_row_stats = [&](int par) {
+        double S1 = 0.0, S2 = 0.0;
+        for (int w = 0; w < (n_group >> 5); ++w) {
+            S1 += sc->wred[par][w][0];
+            S2 += sc->wred[par][w][1];
+        }
+        const double mm = sc->mrow[par];
+        const long long r = sc->prow[par];
+        p.row_stats[2 * r] = S1 - Kd * mm;
+        p.row_stats[2 * r + 1] = fma(Kd * mm, mm, fma(-2.0 * mm, S1, S2));
+    };
     int it = 0;
+    // developer timeline (tools/timeline.py): stamps by thread 0 (group) and by the last warp (run-ahead)
+#define ICNV_STAMP(slot)                                                                                  \
+    do {                                                                                                  \
+        if (p.dbg != nullptr && it < p.dbg_rows && tid == 0)                                              \
+            p.dbg[((size_t)blockIdx.x * p.dbg_rows + it) * 16 + (slot)] = clock64();                       \
+    } while (0)
 
     for (; row < p.n_rows; row += gridDim.x, ++it) {
+        ICNV_STAMP(0);
         // ======================= stage the raw row =======================
         if constexpr (GROUPED) {
             if (tma) {
                 mbar_wait(&sc->mbar, parity);
                 parity ^= 1u;
-            } else if (dense) {
+                ICNV_STAMP(1);
+                    } else if (dense) {
                 const float* src = p.X + row * p.ldx;
                 for (int i = tid; i < p.G; i += NT) raw[i] = __ldg(src + i);
                 __syncthreads();
@@ -386,13 +519,16 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
             // warp-blocks of 32 quads are handed out dynamically: warps that are not in the group arrive
             // here early (they skipped the median of the previous row) and take most of them
             int* next_wb = &sc->next_wb[it & 1];
+#ifdef ICNV_AB_GROUPNOSTEAL
+            while (!in_group || n_group == NT || !tma) {
+#else
             while (true) {
+#endif
                 int wb = 0;
                 if (lane == 0) wb = atomicAdd(next_wb, 1);
                 wb = __shfl_sync(0xffffffffu, wb, 0);
                 if (wb >= n_wb) break;
-                const int quad = (wb << 5) + lane;
-                if (quad >= nquads) continue;
+                const int quad = (wb << 5) + lane;  // slot index; every slot of every warp-block is valid
                 double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
                 // table entry (wb, j, lane, u): ((wb*gs + j)*32 + lane)*4 + u
                 const size_t tbase = ((size_t)wb * gs * 32 + lane) * 4;
@@ -404,7 +540,8 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                     const float4 lo = ldg_nc_f4(lp + j * 128);
                     float4 hi = lo;
                     if constexpr (BOUNDED) hi = ldg_nc_f4(hp + j * 128);
-                    const float x[4] = {lds_f32(raw_s + id.x), lds_f32(raw_s + id.y), lds_f32(raw_s + id.z), lds_f32(raw_s + id.w)};
+                    // table entries are complete shared-window addresses (raw base baked in by the host)
+                    const float x[4] = {lds_f32(id.x), lds_f32(id.y), lds_f32(id.z), lds_f32(id.w)};
                     const float l4[4] = {lo.x, lo.y, lo.z, lo.w};
                     const float h4[4] = {hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
@@ -427,18 +564,24 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 } else {
                     for (int j = 0; j < gs; ++j) body(j, w_c[j]);
                 }
-                // thread's u-th group is u*nquads + quad: for fixed u the lanes store consecutive 16 B
+                // lane l owns groups with g % 8 == l % 8: a quarter-warp's 16-byte stores hit 8 bank groups
+                const int4 gid = __ldg(reinterpret_cast<const int4*>(p.grp_w) + quad);
+                const int gq[4] = {gid.x, gid.y, gid.z, gid.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    AB[u * nquads + quad] = make_double2(a[u], b[u]);
-                    if (qstar >= 0) Cp[u * nquads + quad] = c[u];
+                    AB[gq[u]] = make_double2(a[u], b[u]);
+                    if (qstar >= 0) Cp[gq[u]] = c[u];
                 }
             }
-            __syncthreads();  // gathers done: raw row is dead, partials visible
-            if (tid == 0) {
+            ICNV_STAMP(2);
+                __syncthreads();  // gathers done: raw row is dead, partials visible
+            ICNV_STAMP(3);
+                if (tid == ISSUER) {
                 *next_wb = 0;  // used again two rows from now
                 if (tma && row + gridDim.x < p.n_rows) issue_row(row + gridDim.x);
             }
+            if (tid == 0 && it > 0) finish_row_stats((it - 1) & 1);
+            ICNV_STAMP(13);
         } else {
             // direct tier: position-sorted centred row (float, or double for float64 centring)
             for (int s = tid; s < p.n_sorted; s += NT) {
@@ -470,27 +613,26 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 }
             }
             __syncthreads();
+            if (tid == 0 && it > 0) finish_row_stats((it - 1) & 1);
         }
 
         if (!in_group) {
             __syncthreads();  // partials / sorted row consumed by the group: safe to start the next row
-            continue;
+                continue;
         }
 
         // ======================= windows =======================
         double v[VPT];
-        int nv[TPT], col0[TPT];
+        int nv[TPT];
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
             nv[tt] = 0;
-            col0[tt] = 0;
 #pragma unroll
             for (int i = 0; i < LOUT; ++i) v[tt * LOUT + i] = INFINITY;
             const int ti = tid + tt * NT;
             if (ti < p.n_tasks) {
-                const int4 t = __ldg(reinterpret_cast<const int4*>(p.tasks) + ti);
-                col0[tt] = t.y;
+                const int4 t = task[tt];
                 if ((t.w & 0xFF) == 0) {
                     nv[tt] = t.z;
                     if constexpr (TIER == 0) {
@@ -577,43 +719,67 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
             }
         }
 
-        // ======================= row sums (one fp64 reduction), median, centring =======================
-        s1 = warp_sum_d(s1);
-        s2 = warp_sum_d(s2);
-        if (lane == 0) {
-            sc->wred[warp][0] = s1;
-            sc->wred[warp][1] = s2;
-            if (warp == 0) sc->cand_n = 0;
+        ICNV_STAMP(15);
+        // ======================= bracket estimate, median, centring =======================
+        {
+            const float f1 = warp_sum_f((float)s1), f2 = warp_sum_f((float)s2);
+            if (lane == 0) sc->wsumf[warp] = make_float2(f1, f2);
+            if (warp == 0) {
+                sc->cand[lane] = INFINITY;
+                if (lane == 0) sc->cand_n = 0;
+            }
         }
+        ICNV_STAMP(4);
         __syncthreads();  // CTA-wide: also tells the run-ahead warps that the partials have been read
-        s1 = lane < (n_group >> 5) ? sc->wred[lane][0] : 0.0;
-        s2 = lane < (n_group >> 5) ? sc->wred[lane][1] : 0.0;
-        s1 = warp_sum_d(s1);
-        s2 = warp_sum_d(s2);
-
-        const double m = block_median<VPT>(v, p.K, s1, s2, sc, lane, warp, n_group);
+        float t1 = 0.f, t2 = 0.f;
+        for (int w = 0; w < (n_group >> 5); ++w) {
+            const float2 q = sc->wsumf[w];
+            t1 += q.x;
+            t2 += q.y;
+        }
+        const float invK = 1.f / (float)p.K;
+        const float mean_f = t1 * invK;
+        const float var_f = fmaxf(t2 * invK - mean_f * mean_f, 0.f);
+        ICNV_STAMP(5);
+        long long* mdbg = (p.dbg != nullptr && it < p.dbg_rows && tid == 0) ? p.dbg + ((size_t)blockIdx.x * p.dbg_rows + it) * 16 : nullptr;
+        const double m = block_median<VPT>(v, p.K, mean_f, var_f, sc, lane, warp, n_group, mdbg);
+        ICNV_STAMP(6);
 
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
-            if (p.out_f64) {
-                double* o = reinterpret_cast<double*>(p.out) + row * p.ldo + col0[tt];
+            // tile order: the 32 lanes of a warp write 32 consecutive values per instruction
+            const int ti = tid + tt * NT;
+            const size_t pos = (size_t)row * p.ldo + (size_t)(ti >> 5) * (32 * LOUT) + (ti & 31);
+            if (ti < ((p.n_tasks + 31) & ~31)) {
+                if (p.out_f64) {
+                    double* o = reinterpret_cast<double*>(p.out) + pos;
 #pragma unroll
-                for (int i = 0; i < LOUT; ++i)
-                    if (i < nv[tt]) o[i] = v[tt * LOUT + i] - m;
-            } else {
-                float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0[tt];
+                    for (int i = 0; i < LOUT; ++i) o[i * 32] = v[tt * LOUT + i] - m;
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + pos;
 #pragma unroll
-                for (int i = 0; i < LOUT; ++i)
-                    if (i < nv[tt]) o[i] = (float)(v[tt * LOUT + i] - m);
+                    for (int i = 0; i < LOUT; ++i) o[i * 32] = (float)(v[tt * LOUT + i] - m);
+                }
             }
         }
-        if (tid == 0) {
-            // sum(v - m) and sum((v - m)^2) from the raw moments
-            p.row_stats[2 * row] = s1 - Kd * m;
-            p.row_stats[2 * row + 1] = fma(Kd * m, m, fma(-2.0 * m, s1, s2));
+        // exact row moments: reduced per warp here, finished by thread 0 after the next CTA-wide barrier
+        {
+            const double e1 = warp_sum_d(s1), e2 = warp_sum_d(s2);
+            if (lane == 0) {
+                sc->wred[it & 1][warp][0] = e1;
+                sc->wred[it & 1][warp][1] = e2;
+                if (warp == 0) {
+                    sc->mrow[it & 1] = m;
+                    sc->prow[it & 1] = row;
+                }
+            }
         }
+        ICNV_STAMP(7);
         // the next row's barriers order the reuse of `sc`
     }
+#undef ICNV_STAMP
+    __syncthreads();
+    if (tid == 0 && it > 0) finish_row_stats((it - 1) & 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -671,5 +837,29 @@ int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt
 }
 
 size_t smooth_scratch_bytes() { return SCRATCH_BYTES; }
+
+// Shared-window address of raw[0] for the grouped kernels (dynamic smem base + scratch block).  The host
+// bakes it into the gather table; the kernels trap if their own value differs.
+__global__ void probe_smem_kernel(uint32_t* out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    if (threadIdx.x == 0) *out = smem_u32(smem) & 0xFFFFFFu;
+}
+int smooth_raw_base(uint32_t* base) {
+    static uint32_t cached = 0;
+    static bool have = false;
+    if (!have) {
+        uint32_t* d = nullptr;
+        ICNV_CUDA(cudaMalloc(&d, sizeof(uint32_t)));
+        probe_smem_kernel<<<1, 32, 64>>>(d);
+        ICNV_CUDA(cudaGetLastError());
+        uint32_t h = 0;
+        ICNV_CUDA(cudaMemcpy(&h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        cached = h + (uint32_t)SCRATCH_BYTES;
+        have = true;
+    }
+    *base = cached;
+    return 0;
+}
 
 }  // namespace icnv

@@ -15,6 +15,9 @@ var = cnv.datasets.synthetic_var(G, seed=0)
 Xd = cnv.datasets.device_counts(N, G, dev, seed=1000)
 peak = json.load(open(Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"))["hbm_gbs"] if (Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json").exists() else 6650.0
 
+WINDOWS = [int(w) for w in os.environ.get("QB_WINDOWS", "100,250").split(",")]
+REPS = int(os.environ.get("QB_REPS", "5"))
+
 def timeit(fn, reps=None, warm=2):
     reps = reps or REPS
     warm = min(warm, reps)
@@ -27,8 +30,11 @@ def timeit(fn, reps=None, warm=2):
         ts.append(a.elapsed_time(b))
     return min(ts), float(np.median(ts))
 
-WINDOWS = [int(w) for w in os.environ.get("QB_WINDOWS", "100,250").split(",")]
-REPS = int(os.environ.get("QB_REPS", "5"))
+# box sanity: plain device copy bandwidth (read + write), to spot a slow box
+_a = torch.empty(1 << 28, dtype=torch.float32, device=dev); _b = torch.empty_like(_a)
+_t = timeit(lambda: _b.copy_(_a), reps=5)
+print(json.dumps(dict(box_copy_GBs=2 * _a.numel() * 4 / _t[0] / 1e6)))
+del _a, _b
 for window in WINDOWS:
     layout = build_layout(var, window, 10)
     with DevicePlan(layout, dev) as plan:
@@ -38,10 +44,11 @@ for window in WINDOWS:
         sums, counts = plan.colsum(Xd)
         ref = plan.mean_from_sums(sums, counts)
         plan.set_reference(ref)
+        tmp = torch.empty((N, plan.tmp_width()), dtype=torch.float32, device=dev)
         out = torch.empty((N, K), dtype=torch.float32, device=dev)
         stats = torch.empty((N, 2), dtype=torch.float64, device=dev)
-        t_sm = timeit(lambda: plan.smooth(Xd, 3.0, out=out, row_stats=stats))
-        t_th = timeit(lambda: plan.threshold(out, stats, 5000, 1.5))
+        t_sm = timeit(lambda: plan.smooth(Xd, 3.0, tmp=tmp, row_stats=stats))
+        t_th = timeit(lambda: plan.threshold(tmp, stats, 5000, 1.5, out=out))
         by = N * (4 * G + 4 * K)
         print(json.dumps(dict(window=window, N=N, K=K, launch=info,
               colsum_ms=t_cs, colsum_GBs=N*G*4/t_cs[0]/1e6,
