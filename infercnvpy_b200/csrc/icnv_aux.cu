@@ -34,16 +34,17 @@ __global__ void __launch_bounds__(256) colsum_dense_kernel(const float* __restri
     if (any) {
         int64_t r = r0;
         if (VEC && col[3] < G) {
-            for (; r + 4 <= r1; r += 4) {
-                float4 x[4];
-                bool use[4];
+            constexpr int UR = 8;  // rows in flight per thread
+            for (; r + UR <= r1; r += UR) {
+                float4 x[UR];
+                bool use[UR];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < UR; ++k) {
                     use[k] = row_cat ? (row_cat[r + k] == cat) : true;
                     if (use[k]) x[k] = ldg_stream_f4(X + (r + k) * ldx + col[0]);
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
+                for (int k = 0; k < UR; ++k)
                     if (use[k]) {
                         acc[0] += (double)x[k].x;
                         acc[1] += (double)x[k].y;

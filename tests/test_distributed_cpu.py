@@ -1,0 +1,72 @@
+"""N > 1 host logic on CPU: world_size-2 gloo group (the data path itself has no collective besides the
+single all-reduce of the reference-profile column sums)."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from infercnvpy_b200 import shard_rows
+from infercnvpy_b200._engine import allreduce_sums
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_rows, chunk, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)
+        X = rng.poisson(0.3, size=(n_rows, 37)).astype(np.float32)
+        cat = rng.integers(-1, 2, size=n_rows)  # -1 = not a reference cell
+        r0, r1 = shard_rows(n_rows, chunk, rank, world)
+        # what icnv_colsum_* produces for this shard: per-category float64 sums and int64 counts
+        sums = np.stack([X[r0:r1][cat[r0:r1] == c].sum(axis=0, dtype=np.float64) for c in (0, 1)])
+        counts = np.array([(cat[r0:r1] == c).sum() for c in (0, 1)], dtype=np.int64)
+        s, c = allreduce_sums(torch.from_numpy(sums), torch.from_numpy(counts))
+        want_s = np.stack([X[cat == k].sum(axis=0, dtype=np.float64) for k in (0, 1)])
+        want_c = np.array([(cat == k).sum() for k in (0, 1)])
+        np.testing.assert_allclose(s.numpy(), want_s, rtol=1e-13)
+        np.testing.assert_array_equal(c.numpy(), want_c)
+        # every rank ends up with the same profile, equal to the single-process mean
+        ref = (s / c[:, None].to(torch.float64)).numpy()
+        np.testing.assert_allclose(ref, np.stack([X[cat == k].mean(axis=0, dtype=np.float64) for k in (0, 1)]), rtol=1e-12)
+        np.save(os.path.join(out_dir, f"rows_{rank}.npy"), np.array([r0, r1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rows,chunk", [(1000, 128), (257, 100), (90, 100)])
+def test_allreduce_and_sharding_world2(tmp_path, n_rows, chunk):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, n_rows, chunk, str(tmp_path)), nprocs=2, join=True)
+    a, b = (np.load(tmp_path / f"rows_{r}.npy") for r in (0, 1))
+    assert a[0] == 0 and a[1] == b[0] and b[1] == n_rows  # contiguous cover
+    assert a[1] % chunk == 0 or a[1] == n_rows            # cut on a chunk boundary (tl/_infercnv.py:123)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_shard_rows_partition(world):
+    for n_rows, chunk in [(1_000_000, 5000), (100_000, 5000), (12_345, 5000), (3, 5000), (0, 5000)]:
+        pieces = [shard_rows(n_rows, chunk, r, world) for r in range(world)]
+        assert pieces[0][0] == 0 and pieces[-1][1] == n_rows
+        for (a0, a1), (b0, b1) in zip(pieces, pieces[1:]):
+            assert a1 == b0 and a0 <= a1
+        for r0, r1 in pieces:
+            assert r0 % chunk == 0 or r0 == n_rows
+        sizes = [(r1 - r0 + chunk - 1) // chunk for r0, r1 in pieces]
+        assert max(sizes) - min(sizes) <= 1  # chunks are spread evenly
+
+
+def test_single_process_is_identity():
+    s, c = torch.ones(2, 3, dtype=torch.float64), torch.ones(2, dtype=torch.int64)
+    s2, c2 = allreduce_sums(s, c)
+    assert s2 is s and c2 is c

@@ -1,0 +1,82 @@
+"""Host-side logic and the C-ABI surface, no GPU needed."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import infercnvpy_b200 as cnv
+from infercnvpy_b200 import _lib
+from infercnvpy_b200._layout import build_layout
+from oracle import infercnv_oracle as orc
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "icnv.h").read_text()
+    declared = set(re.findall(r"\b(icnv_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and include/icnv.h disagree"
+    lib_path = _lib.lib_path()
+    assert lib_path.exists(), "run __graft_entry__.build() first"
+    handle = ctypes.CDLL(str(lib_path))
+    for name in declared:
+        assert hasattr(handle, name), f"{name} not exported"
+    handle.icnv_version.restype = ctypes.c_int
+    assert handle.icnv_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    var = cnv.datasets.synthetic_var(300, seed=1)
+    X = cnv.datasets.synthetic_counts(4, 300, seed=1)
+    with pytest.raises(_lib.IcnvError, match="CUDA"):
+        cnv.tl.infercnv(cnv.AnnData(X, var=var))
+
+
+@pytest.mark.parametrize("window,step,extras", [(100, 10, True), (250, 10, False), (11, 1, True), (20, 3, False), (5000, 10, True)])
+def test_layout_matches_oracle_indices(window, step, extras):
+    """chr_pos / gene permutation are integers and must match the oracle exactly."""
+    var = cnv.datasets.synthetic_var(2400, seed=4, with_extras=extras)
+    lay = build_layout(var, window, step)
+    X = np.zeros((1, 2400), dtype=np.float32)
+    chr_pos, res = orc.infercnv(X, var["chromosome"].values, var["start"].values, window_size=window, step=step, dynamic_threshold=None)
+    assert list(chr_pos) == lay.chromosomes
+    assert {k: int(v) for k, v in chr_pos.items()} == {k: int(v) for k, v in lay.chr_pos.items()}
+    assert res.shape[1] == lay.n_out
+    keep = ~lay.var_mask
+    chrom_k, start_k = var["chromosome"].values[keep], var["start"].values[keep]
+    kept_cols = np.flatnonzero(keep)
+    for i, c in enumerate(lay.chromosomes):
+        want = kept_cols[orc.gene_order(chrom_k, start_k, c)]
+        np.testing.assert_array_equal(lay.gene_idx[lay.seg_off[i] : lay.seg_off[i + 1]], want)
+
+
+def test_layout_ties_follow_pandas():
+    var = pd.DataFrame({"chromosome": ["chr1"] * 40, "start": [5] * 20 + [1] * 20, "end": 0}, index=[f"g{i}" for i in range(40)])
+    lay = build_layout(var, 3, 1)
+    want = var.loc[var["chromosome"] == "chr1"].sort_values("start").index.map(lambda s: int(s[1:])).to_numpy()
+    np.testing.assert_array_equal(lay.gene_idx, want)
+
+
+def test_layout_errors():
+    var = cnv.datasets.synthetic_var(50, seed=0)
+    with pytest.raises(ValueError, match="Genomic positions not found"):
+        build_layout(var.drop(columns=["end"]), 10, 1)
+    with pytest.raises(ValueError):
+        build_layout(var, 0, 1)
+
+
+def test_duck_anndata_slicing():
+    var = cnv.datasets.synthetic_var(30, seed=0)
+    a = cnv.AnnData(np.arange(60, dtype=np.float32).reshape(2, 30), var=var)
+    b = a[:, np.arange(30) % 2 == 0]
+    assert b.shape == (2, 15) and list(b.var_names) == list(var.index[::2])
+    assert a.copy().X is not a.X
