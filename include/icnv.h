@@ -140,6 +140,33 @@ int icnv_rowabs_dense(const void* X, int32_t is_f64, int64_t n_rows, int64_t K, 
 int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_rows, int32_t n_labels,
                     double* label_sum, int64_t* label_rows, void* stream);
 
+/* --------------------------------------------- pca / neighbors / leiden ----
+ * The reference hands these steps to scanpy (tl/__init__.py:13-75, pp/__init__.py:8-43 ->
+ * scikit-learn TruncatedSVD(arpack), exact/approximate kNN + umap-learn fuzzy_simplicial_set,
+ * leidenalg); the entry points below are the device pieces our wrappers are built from.
+ * Parity is unpinned (no reference test asserts anything here). */
+/* CSR (float32 / float64 values) -> dense float32 [n_rows, ld] */
+int icnv_csr_to_dense_f32(const int64_t* indptr, const int32_t* indices, const void* data, int32_t data_is_f64,
+                          int64_t n_rows, int32_t K, float* dense, int64_t ld, void* stream);
+/* C [K, K] float64 = X^T X of this row shard (OVERWRITTEN; all-reduce across shards) */
+int icnv_gram_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, double* C, void* stream);
+/* Y [n_rows, n_comp] float32 = (X - mu) V;  V [K, n_comp] float64 row-major, mu [K] float64 or NULL */
+int icnv_project_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, const double* V, int32_t n_comp,
+                     const double* mu, float* Y, void* stream);
+/* exact euclidean kNN of rows [q0, q0+nq) of P [n_all, d] float32 against all rows: KK = 16 (k <= 16) or 32
+ * neighbours per query, ascending squared distance, ties by index; knn_idx/knn_d2 are [nq, KK] */
+int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx,
+                 float* knn_d2, void* stream);
+/* umap-learn smooth_knn_dist + membership strengths per row; dist/idx/vals are [n, k] */
+int icnv_fuzzy_rows(const float* dist, const int32_t* idx, int64_t n, int32_t k, int64_t row0, float mean_all,
+                    float* vals, float* sigma, float* rho, void* stream);
+/* weighted degree of a CSR graph, and one synchronous local-moving sweep of RB-configuration modularity
+ * (ctot is scratch [n]; n_moved receives the number of nodes that changed community) */
+int icnv_weighted_degree(const int64_t* indptr, const float* w, int64_t n, double* kdeg, void* stream);
+int icnv_louvain_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg,
+                       const int32_t* comm, double* ctot, int64_t n, double two_m, double gamma, int32_t sweep,
+                       int32_t* comm_new, int32_t* n_moved, void* stream);
+
 /* Launch geometry of the smoothing kernel chosen for this plan (for the bench
  * and the ncu notes): CTAs per SM, threads, dynamic shared memory bytes. */
 int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* threads, int32_t* smem_bytes,

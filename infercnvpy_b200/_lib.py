@@ -39,6 +39,13 @@ SIGNATURES = {
     "icnv_dense_to_csr": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_rowabs_csr": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_rowabs_dense": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "icnv_csr_to_dense_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, C.c_int64, C.c_int32, c_vp, C.c_int64, c_vp]),
+    "icnv_gram_f32": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32, c_vp, c_vp]),
+    "icnv_project_f32": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32, c_vp, C.c_int32, c_vp, c_vp, c_vp]),
+    "icnv_knn_f32": (C.c_int, [c_vp, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, c_vp, c_vp, c_vp]),
+    "icnv_fuzzy_rows": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int32, C.c_int64, C.c_float, c_vp, c_vp, c_vp, c_vp]),
+    "icnv_weighted_degree": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
+    "icnv_louvain_sweep": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, C.c_double, C.c_int32, c_vp, c_vp, c_vp]),
     "icnv_debug_set_timeline": (C.c_int, [c_vp, C.c_int]),
     "icnv_label_sums": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int32, c_vp, c_vp, c_vp]),
 }

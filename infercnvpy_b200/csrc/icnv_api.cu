@@ -31,6 +31,14 @@ int aux_rowabs_csr(const int64_t*, const void*, bool, int64_t, double*, cudaStre
 int aux_rowabs_dense(const void*, bool, int64_t, int64_t, int64_t, double*, cudaStream_t);
 int aux_label_sums(const double*, const int32_t*, int64_t, int, double*, int64_t*, cudaStream_t);
 size_t smooth_scratch_bytes();
+int graph_csr_to_dense(const int64_t*, const int32_t*, const void*, bool, int64_t, int, float*, int64_t, cudaStream_t);
+int graph_gram(const float*, int64_t, int64_t, int, double*, cudaStream_t);
+int graph_project(const float*, int64_t, int64_t, int, const double*, int, const double*, float*, cudaStream_t);
+int graph_knn(const float*, int64_t, int, int64_t, int64_t, int, int32_t*, float*, cudaStream_t);
+int graph_fuzzy_rows(const float*, const int32_t*, int64_t, int, int64_t, float, float*, float*, float*, cudaStream_t);
+int graph_weighted_degree(const int64_t*, const float*, int64_t, double*, cudaStream_t);
+int graph_louvain_sweep(const int64_t*, const int32_t*, const float*, const double*, const int32_t*, double*, int64_t, double, double,
+                        int, int32_t*, int32_t*, cudaStream_t);
 
 template <typename T>
 struct DevBuf {
@@ -653,6 +661,41 @@ int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_
                     int64_t* label_rows, void* stream) {
     if (!row_abs_sum || !labels || !label_sum || !label_rows) return ICNV_EINVAL;
     return aux_label_sums(row_abs_sum, labels, n_rows, n_labels, label_sum, label_rows, (cudaStream_t)stream);
+}
+
+int icnv_csr_to_dense_f32(const int64_t* indptr, const int32_t* indices, const void* data, int32_t data_is_f64, int64_t n_rows,
+                          int32_t K, float* dense, int64_t ld, void* stream) {
+    if (!indptr || !dense || ld < K) return ICNV_EINVAL;
+    return graph_csr_to_dense(indptr, indices, data, data_is_f64 != 0, n_rows, K, dense, ld, (cudaStream_t)stream);
+}
+int icnv_gram_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, double* C, void* stream) {
+    if (!X || !C || K < 1 || ld < K) return ICNV_EINVAL;
+    return graph_gram(X, n_rows, ld, K, C, (cudaStream_t)stream);
+}
+int icnv_project_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, const double* V, int32_t n_comp, const double* mu,
+                     float* Y, void* stream) {
+    if (!X || !V || !Y || n_comp < 1) return ICNV_EINVAL;
+    return graph_project(X, n_rows, ld, K, V, n_comp, mu, Y, (cudaStream_t)stream);
+}
+int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx, float* knn_d2,
+                 void* stream) {
+    if (!P || !knn_idx || !knn_d2 || q0 < 0 || q0 + nq > n_all) return ICNV_EINVAL;
+    return graph_knn(P, n_all, d, q0, nq, k, knn_idx, knn_d2, (cudaStream_t)stream);
+}
+int icnv_fuzzy_rows(const float* dist, const int32_t* idx, int64_t n, int32_t k, int64_t row0, float mean_all, float* vals,
+                    float* sigma, float* rho, void* stream) {
+    if (!dist || !idx || !vals || !sigma || !rho || k < 2) return ICNV_EINVAL;
+    return graph_fuzzy_rows(dist, idx, n, k, row0, mean_all, vals, sigma, rho, (cudaStream_t)stream);
+}
+int icnv_weighted_degree(const int64_t* indptr, const float* w, int64_t n, double* kdeg, void* stream) {
+    if (!indptr || !kdeg) return ICNV_EINVAL;
+    return graph_weighted_degree(indptr, w, n, kdeg, (cudaStream_t)stream);
+}
+int icnv_louvain_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg, const int32_t* comm,
+                       double* ctot, int64_t n, double two_m, double gamma, int32_t sweep, int32_t* comm_new, int32_t* n_moved,
+                       void* stream) {
+    if (!indptr || !kdeg || !comm || !ctot || !comm_new || !n_moved || !(two_m > 0)) return ICNV_EINVAL;
+    return graph_louvain_sweep(indptr, indices, w, kdeg, comm, ctot, n, two_m, gamma, sweep, comm_new, n_moved, (cudaStream_t)stream);
 }
 
 }  // extern "C"

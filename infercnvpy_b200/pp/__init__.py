@@ -1,3 +1,5 @@
-"""Preprocessing: ``cnv.pp.*`` (reference: ``/root/reference/src/infercnvpy/pp/__init__.py``)."""
+"""Preprocessing: ``cnv.pp.neighbors`` (reference: ``/root/reference/src/infercnvpy/pp/__init__.py:8-43``)."""
 
-__all__: list[str] = []
+from ._neighbors import neighbors
+
+__all__ = ["neighbors"]
