@@ -459,11 +459,22 @@ int icnv_colsum_dense_f32(const float* X, int64_t n_rows, int64_t ldx, int32_t G
     }
     // row splits: enough CTAs to fill the machine, each with a decent run of rows
     int n_split = (int)std::min<int64_t>(std::max<int64_t>(1, n_rows / 64), 4 * 148 / std::max(1, (G + 1023) / 1024) + 1);
-    double* partial = nullptr;
-    ICNV_CUDA(cudaMallocAsync(&partial, sizeof(double) * (size_t)n_split * n_cat * G, (cudaStream_t)stream));
-    int rc = aux_colsum_dense(X, n_rows, ldx, G, row_cat, n_cat, sums, counts, partial, n_split, (cudaStream_t)stream);
-    cudaFreeAsync(partial, (cudaStream_t)stream);
-    return rc;
+    // grow-only per-device workspace for the [split][cat][G] partial sums (stream-ordered use only)
+    static double* ws[16] = {nullptr};
+    static size_t ws_bytes[16] = {0};
+    int devi = 0;
+    ICNV_CUDA(cudaGetDevice(&devi));
+    const size_t need = sizeof(double) * (size_t)n_split * n_cat * G;
+    if (devi < 0 || devi >= 16) {
+        set_error("icnv_colsum_dense_f32: device index out of range");
+        return ICNV_EINVAL;
+    }
+    if (ws_bytes[devi] < need) {
+        if (ws[devi]) ICNV_CUDA(cudaFree(ws[devi]));
+        ICNV_CUDA(cudaMalloc(&ws[devi], need));
+        ws_bytes[devi] = need;
+    }
+    return aux_colsum_dense(X, n_rows, ldx, G, row_cat, n_cat, sums, counts, ws[devi], n_split, (cudaStream_t)stream);
 }
 
 int icnv_colsum_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows, int32_t G,
