@@ -261,12 +261,13 @@ def main():
         ref = plan.mean_from_sums(sums, counts)             # 1
         plan.set_reference(ref)                             # 1
         if "tmp" not in tmp_holder:
-            tmp_holder["tmp"] = torch.empty((n_local, plan.tmp_width()), dtype=torch.float32, device=dev)
+            tmp_holder["tmp"] = torch.empty((n_local, plan.tmp_width()), dtype=torch.float64, device=dev)
         ev_s0[i].record()
-        plan.smooth(Xin, LFC, tmp=tmp_holder["tmp"], row_stats=stats)     # 1  <- dominant kernel
+        plan.smooth(Xin, LFC, tmp=tmp_holder["tmp"])        # 1  <- dominant kernel (steps 1-3)
         ev_s1[i].record()
-        _, thr, row_abs, row_nnz = plan.threshold(tmp_holder["tmp"], stats, CHUNK, DYN, out=out)   # 2
-        launches["n"] += 8 if container == "dense" else 7
+        plan.center(tmp_holder["tmp"], out=out, row_stats=stats)             # 1  (step 4: exact row median)
+        thr, row_abs, row_nnz = plan.threshold(out, stats, CHUNK, DYN)       # 2  (step 5)
+        launches["n"] += 9 if container == "dense" else 8
         return row_abs
 
     def barrier():

@@ -90,37 +90,34 @@ int icnv_nnz_to_indptr(const int32_t* row_nnz, int64_t n_rows, int64_t* indptr, 
 int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int32_t ref_is_f64, void* stream);
 
 /* ------------------------------------------------------------- smoothing ----
- * Steps 1-4 of tl/_infercnv.py:411-442 for n_rows cells: centre, clip to
- * +-lfc_clip, per-chromosome pyramid running mean decimated by `step`
- * (:179-244, :301-356), subtract the row median.
- *   out        INTERMEDIATE [n_rows, ldo] float32 (out_is_f64 == 0) or float64,
- *              ldo >= icnv_plan_tmp_width().  Its columns are in the kernel's
- *              warp-tile order (so that every store is a full 128-byte line);
- *              icnv_apply_threshold turns it into the natural [n_rows, K] matrix.
- *   row_stats  [n_rows, 2] float64: sum and sum of squares of the row
- *              (inputs of the per-chunk std of :450)
+ * Steps 1-3 of tl/_infercnv.py:411-440 for n_rows cells: centre (:422-432), clip to +-lfc_clip (:436),
+ * per-chromosome pyramid running mean decimated by `step` (:179-244, :301-356).
+ *   tmp   [n_rows, ld_tmp >= icnv_plan_tmp_width()] float64: the smoothed rows in the kernel's warp-tile
+ *         column order (every store a full line); icnv_center_rows turns them into the natural matrix.
  */
 int icnv_plan_tmp_width(const icnv_plan* plan, int64_t* ld_tmp);
 int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip,
-                          void* out, int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream);
+                          double* tmp, int64_t ld_tmp, void* stream);
 int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* indices, const float* data,
-                        int64_t n_rows, double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo,
-                        double* row_stats, void* stream);
+                        int64_t n_rows, double lfc_clip, double* tmp, int64_t ld_tmp, void* stream);
 
-/* Step 5, tl/_infercnv.py:449-451.  Rows are cut into consecutive chunks of
- * chunk_rows (the reference's `chunksize`, :123); thr[c] = dyn_thr *
- * population-std over every element of chunk c.  thr has ceil(n_rows /
- * chunk_rows) entries. */
+/* Step 4, tl/_infercnv.py:442: subtract the exact row median (np.median: mean of the two middle values
+ * for even K).  tmp -> out [n_rows, ldo >= K] float32 (out_is_f64 == 0) or float64, natural column order;
+ * row_stats [n_rows, 2] float64 = sum and sum of squares of the centred row (inputs of :450). */
+int icnv_center_rows(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t ld_tmp, void* out,
+                     int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream);
+
+/* Step 5, tl/_infercnv.py:449-451.  Rows are cut into consecutive chunks of chunk_rows (the reference's
+ * `chunksize`, :123); thr[c] = dyn_thr * population-std over every element of chunk c.  thr has
+ * ceil(n_rows / chunk_rows) entries. */
 int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int64_t chunk_rows, double dyn_thr,
                          double* thr, void* stream);
-/* tmp (intermediate of icnv_smooth_*) -> out [n_rows, ldo >= K] in natural column
- * order with |v| < thr[chunk of row] zeroed (strict, :451); also emits per row
- * sum|v| and the number of non-zeros (inputs of cnv_score, tl/_scores.py:66, and
- * of the CSR conversion, tl/_infercnv.py:455).  thr == NULL: no zeroing (the
- * pre-threshold matrix, dynamic_threshold=None). */
-int icnv_apply_threshold(icnv_plan* plan, const void* tmp, int32_t is_f64, int64_t n_rows, int64_t ld_tmp,
-                         int64_t chunk_rows, const double* thr, void* out, int64_t ldo, double* row_abs_sum,
-                         int32_t* row_nnz, void* stream);
+/* Zero |v| < thr[chunk of row] in place (strict, :451); also emits per row sum|v| and the number of
+ * non-zeros (inputs of cnv_score, tl/_scores.py:66, and of the CSR conversion, tl/_infercnv.py:455).
+ * thr == NULL: no zeroing, statistics only. */
+int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo,
+                         int64_t chunk_rows, const double* thr, double* row_abs_sum, int32_t* row_nnz,
+                         void* stream);
 
 /* Dense [n_rows, K] -> CSR (tl/_infercnv.py:455).  indptr [n_rows+1] int64 must
  * already hold the exclusive prefix sum of row_nnz; indices int32; data float32

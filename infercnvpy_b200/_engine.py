@@ -139,50 +139,54 @@ class DevicePlan:
         _lib.check(self.lib.icnv_plan_tmp_width(self.handle, C.byref(w)), "icnv_plan_tmp_width")
         return int(w.value)
 
-    def smooth(self, X, lfc_clip: float, tmp=None, row_stats=None, out_dtype=None):
-        """Steps 1-4 for the rows of ``X`` -> ``(tmp [n, tmp_width], row_stats [n, 2])``.
-
-        ``tmp`` is the kernel's intermediate in warp-tile column order; ``threshold`` turns it into
-        the natural ``[n, K]`` matrix (with or without the noise filter)."""
+    def smooth(self, X, lfc_clip: float, tmp=None):
+        """Steps 1-3 for the rows of ``X`` -> ``tmp [n, tmp_width]`` float64 (smoothed rows, warp-tile order)."""
         torch = _torch()
-        out_dtype = out_dtype or torch.float32
-        if isinstance(X, tuple):
-            n = X[0].numel() - 1
-        else:
-            n = X.shape[0]
+        n = X[0].numel() - 1 if isinstance(X, tuple) else X.shape[0]
         if tmp is None:
-            tmp = torch.empty((n, self.tmp_width()), dtype=out_dtype, device=self.device)
-        if row_stats is None:
-            row_stats = torch.empty((n, 2), dtype=torch.float64, device=self.device)
-        is64 = int(tmp.dtype == torch.float64)
+            tmp = torch.empty((n, self.tmp_width()), dtype=torch.float64, device=self.device)
+        assert tmp.dtype == torch.float64
         ld = tmp.stride(0) if n else self.tmp_width()
         if isinstance(X, tuple):
             indptr, indices, data = X
             rc = self.lib.icnv_smooth_csr_f32(
-                self.handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), n, float(lfc_clip), _lib.ptr(tmp), is64,
-                ld, _lib.ptr(row_stats), self._stream(),
+                self.handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), n, float(lfc_clip), _lib.ptr(tmp), ld, self._stream()
             )
         else:
             assert X.dtype == torch.float32 and X.stride(1) == 1
             rc = self.lib.icnv_smooth_dense_f32(
-                self.handle, _lib.ptr(X), n, X.stride(0), float(lfc_clip), _lib.ptr(tmp), is64, ld, _lib.ptr(row_stats),
-                self._stream(),
+                self.handle, _lib.ptr(X), n, X.stride(0), float(lfc_clip), _lib.ptr(tmp), ld, self._stream()
             )
         _lib.check(rc, "icnv_smooth")
-        return tmp, row_stats
+        return tmp
 
-    def threshold(self, tmp, row_stats, chunk_rows: int, dynamic_threshold, out=None):
-        """Step 5: ``tmp`` -> natural-order ``out [n, K]`` with the per-chunk noise filter applied
-        (``dynamic_threshold=None``: no filter).  Returns ``(out, thr or None, row_abs_sum, row_nnz)``."""
+    def center(self, tmp, out=None, row_stats=None, out_dtype=None):
+        """Step 4: exact row median + centring: ``tmp`` -> ``(out [n, K] natural order, row_stats [n, 2])``."""
         torch = _torch()
         n = tmp.shape[0]
-        K = self.K
         if out is None:
-            out = torch.empty((n, K), dtype=tmp.dtype, device=self.device)
+            out = torch.empty((n, self.K), dtype=out_dtype or torch.float32, device=self.device)
+        if row_stats is None:
+            row_stats = torch.empty((n, 2), dtype=torch.float64, device=self.device)
+        if n:
+            _lib.check(
+                self.lib.icnv_center_rows(
+                    self.handle, _lib.ptr(tmp), n, tmp.stride(0), _lib.ptr(out), int(out.dtype == torch.float64), out.stride(0),
+                    _lib.ptr(row_stats), self._stream(),
+                ),
+                "icnv_center_rows",
+            )
+        return out, row_stats
+
+    def threshold(self, out, row_stats, chunk_rows: int, dynamic_threshold):
+        """Step 5 in place on ``out`` (``dynamic_threshold=None``: statistics only).
+        Returns ``(thr or None, row_abs_sum, row_nnz)``."""
+        torch = _torch()
+        n, K = out.shape
         row_abs = torch.empty((n,), dtype=torch.float64, device=self.device)
         row_nnz = torch.empty((n,), dtype=torch.int32, device=self.device)
         thr = None
-        is64 = int(tmp.dtype == torch.float64)
+        is64 = int(out.dtype == torch.float64)
         if dynamic_threshold is not None and n > 0:
             n_chunks = math.ceil(n / chunk_rows)
             thr = torch.empty((n_chunks,), dtype=torch.float64, device=self.device)
@@ -193,12 +197,11 @@ class DevicePlan:
         if n > 0:
             _lib.check(
                 self.lib.icnv_apply_threshold(
-                    self.handle, _lib.ptr(tmp), is64, n, tmp.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(out), out.stride(0),
-                    _lib.ptr(row_abs), _lib.ptr(row_nnz), self._stream(),
+                    _lib.ptr(out), is64, n, K, out.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(row_abs), _lib.ptr(row_nnz), self._stream()
                 ),
                 "icnv_apply_threshold",
             )
-        return out, thr, row_abs, row_nnz
+        return thr, row_abs, row_nnz
 
     def to_csr(self, out, row_nnz):
         """Dense thresholded block -> device CSR ``(indptr int64, indices int32, data)``."""

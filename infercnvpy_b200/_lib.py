@@ -31,10 +31,11 @@ SIGNATURES = {
     "icnv_mean_from_sums": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, c_vp, C.c_int32, c_vp]),
     "icnv_nnz_to_indptr": (C.c_int, [c_vp, C.c_int64, c_vp, c_vp]),
     "icnv_plan_set_reference": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int32, c_vp]),
-    "icnv_smooth_dense_f32": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
-    "icnv_smooth_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
+    "icnv_smooth_dense_f32": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_double, c_vp, C.c_int64, c_vp]),
+    "icnv_smooth_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, c_vp, C.c_int64, c_vp]),
+    "icnv_center_rows": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_chunk_threshold": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_vp, c_vp]),
-    "icnv_apply_threshold": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "icnv_apply_threshold": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_plan_tmp_width": (C.c_int, [c_vp, c_i64p]),
     "icnv_dense_to_csr": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_rowabs_csr": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),

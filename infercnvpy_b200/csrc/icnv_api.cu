@@ -24,7 +24,8 @@ int aux_mean_from_sums(const double*, const int64_t*, int, int, void*, bool, cud
 int aux_nnz_to_indptr(const int32_t*, int64_t, int64_t*, cudaStream_t);
 int aux_build_bounds(const void*, bool, int, int, const int32_t*, int64_t, void*, void*, bool, cudaStream_t);
 int aux_chunk_threshold(const double*, int64_t, int64_t, int64_t, double, double*, cudaStream_t);
-int aux_finalize(const void*, bool, int64_t, int64_t, const Task*, int, int64_t, const double*, void*, int64_t, double*, int32_t*, cudaStream_t);
+int aux_center_rows(const double*, int64_t, int64_t, const Task*, int, int, void*, bool, int64_t, double*, cudaStream_t);
+int aux_apply_threshold(void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
 int smooth_raw_base(uint32_t* base);
 int aux_dense_to_csr(const void*, bool, int64_t, int64_t, int64_t, const int64_t*, int32_t*, void*, cudaStream_t);
 int aux_rowabs_csr(const int64_t*, const void*, bool, int64_t, double*, cudaStream_t);
@@ -528,13 +529,12 @@ extern "C" int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta) {
     return ICNV_OK;
 }
 
-static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo,
-                         double* row_stats, void* stream) {
+static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, double* out, int64_t ldo, void* stream) {
     if (!plan->have_ref) {
         set_error("smooth: icnv_plan_set_reference has not been called");
         return ICNV_EINVAL;
     }
-    if (!out || !row_stats || !(lfc_clip >= 0)) {
+    if (!out || !(lfc_clip >= 0)) {
         set_error("smooth: bad argument");
         return ICNV_EINVAL;
     }
@@ -584,8 +584,6 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     sp.K = (int32_t)plan->K;
     sp.out = out;
     sp.ldo = ldo;
-    sp.out_f64 = out_is_f64;
-    sp.row_stats = row_stats;
     sp.dbg = g_dbg_ptr;
     sp.dbg_rows = g_dbg_rows;
     sp.use_tma = sp.X && (sp.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp.X) & 15) == 0) && (plan->G % 4 == 0);
@@ -600,8 +598,8 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, voi
     return smooth_launch(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, sp, grid, ch.smem, (cudaStream_t)stream);
 }
 
-int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip, void* out,
-                          int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream) {
+int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip, double* tmp,
+                          int64_t ld_tmp, void* stream) {
     if (!plan || !X || n_rows < 0 || ldx < plan->G) {
         set_error("icnv_smooth_dense_f32: bad argument");
         return ICNV_EINVAL;
@@ -611,11 +609,11 @@ int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64
     sp.X = X;
     sp.ldx = ldx;
     sp.n_rows = n_rows;
-    return smooth_common(plan, sp, lfc_clip, out, out_is_f64, ldo, row_stats, stream);
+    return smooth_common(plan, sp, lfc_clip, tmp, ld_tmp, stream);
 }
 
 int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
-                        double lfc_clip, void* out, int32_t out_is_f64, int64_t ldo, double* row_stats, void* stream) {
+                        double lfc_clip, double* tmp, int64_t ld_tmp, void* stream) {
     if (!plan || !indptr || n_rows < 0) {
         set_error("icnv_smooth_csr_f32: bad argument");
         return ICNV_EINVAL;
@@ -626,7 +624,22 @@ int icnv_smooth_csr_f32(icnv_plan* plan, const int64_t* indptr, const int32_t* i
     sp.indices = indices;
     sp.data = data;
     sp.n_rows = n_rows;
-    return smooth_common(plan, sp, lfc_clip, out, out_is_f64, ldo, row_stats, stream);
+    return smooth_common(plan, sp, lfc_clip, tmp, ld_tmp, stream);
+}
+
+int icnv_center_rows(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t ld_tmp, void* out, int32_t out_is_f64, int64_t ldo,
+                     double* row_stats, void* stream) {
+    if (!plan || !tmp || !out || !row_stats || ldo < plan->K) {
+        set_error("icnv_center_rows: bad argument");
+        return ICNV_EINVAL;
+    }
+    if (n_rows == 0 || plan->K == 0) return ICNV_OK;
+    Choice ch;
+    int rc = choose(*plan, plan->c64, &ch);
+    if (rc) return rc;
+    const Task* tasks = ch.tier < 2 ? plan->tasks_g.ptr : plan->tasks_d.ptr;
+    const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+    return aux_center_rows(tmp, n_rows, ld_tmp, tasks, n_tasks, (int)plan->K, out, out_is_f64 != 0, ldo, row_stats, (cudaStream_t)stream);
 }
 
 int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int64_t chunk_rows, double dyn_thr, double* thr,
@@ -638,19 +651,13 @@ int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int
     return aux_chunk_threshold(row_stats, n_rows, K, chunk_rows, dyn_thr, thr, (cudaStream_t)stream);
 }
 
-int icnv_apply_threshold(icnv_plan* plan, const void* tmp, int32_t is_f64, int64_t n_rows, int64_t ld_tmp, int64_t chunk_rows,
-                         const double* thr, void* out, int64_t ldo, double* row_abs_sum, int32_t* row_nnz, void* stream) {
-    if (!plan || !tmp || !out || chunk_rows < 1 || ldo < plan->K) {
+int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                         const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream) {
+    if (!out || chunk_rows < 1 || ldo < K) {
         set_error("icnv_apply_threshold: bad argument");
         return ICNV_EINVAL;
     }
-    Choice ch;
-    int rc = choose(*plan, plan->c64, &ch);
-    if (rc) return rc;
-    const Task* tasks = ch.tier < 2 ? plan->tasks_g.ptr : plan->tasks_d.ptr;
-    const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
-    return aux_finalize(tmp, is_f64 != 0, n_rows, ld_tmp, tasks, n_tasks, chunk_rows, thr, out, ldo, row_abs_sum, row_nnz,
-                        (cudaStream_t)stream);
+    return aux_apply_threshold(out, out_is_f64 != 0, n_rows, K, ldo, chunk_rows, thr, row_abs_sum, row_nnz, (cudaStream_t)stream);
 }
 
 int icnv_dense_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, const int64_t* indptr,

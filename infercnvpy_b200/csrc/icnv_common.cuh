@@ -71,12 +71,11 @@ struct SmoothParams {
     const Task* tasks;
     int32_t n_tasks;
     int32_t K;
-    // intermediate [n_rows, ldo] in warp-tile order: value i of task t sits at (t/32)*32*LOUT + i*32 + t%32,
-    // so every store instruction of a warp writes 128 contiguous bytes; icnv_apply_threshold un-permutes
-    void* out;
+    // smoothed rows [n_rows, ldo] fp64 in warp-tile order: value i of task t sits at (t/32)*32*LOUT + i*32 + t%32
+    // (+inf in unused slots), so every store instruction of a warp writes 256 contiguous bytes;
+    // icnv_center_rows un-permutes while it centres
+    double* out;
     int64_t ldo;
-    int32_t out_f64;
-    double* row_stats;
     // optional developer timeline: [grid][dbg_rows][16] clock64 stamps (nullptr = off)
     long long* dbg;
     int32_t dbg_rows;

@@ -23,7 +23,7 @@ def _block_rows(n_rows: int, n_genes: int, n_out: int, chunksize: int) -> int:
     """Rows per device block: a multiple of ``chunksize`` (so every per-chunk std sees a whole
     chunk, _infercnv.py:123,450) that keeps input + output under ICNV_BLOCK_BYTES (default 16 GiB)."""
     budget = int(os.environ.get("ICNV_BLOCK_BYTES", 16 << 30))
-    per_row = 4 * n_genes + 10 * n_out + 64
+    per_row = 4 * n_genes + 14 * n_out + 64
     chunks = max(1, (budget // per_row) // chunksize)
     return min(n_rows, chunks * chunksize) if n_rows else 0
 
@@ -318,9 +318,10 @@ def infercnv(
             Xb = resident if resident is not None else _rows_to_device(expr, r0, r1, device)
             if isinstance(Xb, tuple) and plan.tier == 2:
                 Xb = _densify(Xb, n_genes, device)
-            tmp, stats = plan.smooth(Xb, lfc_clip)
-            out, _, _, row_nnz = plan.threshold(tmp, stats, chunksize, dynamic_threshold)
+            tmp = plan.smooth(Xb, lfc_clip)
+            out, stats = plan.center(tmp)
             del tmp
+            _, _, row_nnz = plan.threshold(out, stats, chunksize, dynamic_threshold)
             indptr, indices, data = plan.to_csr(out, row_nnz)
             parts.append(_host_csr(indptr, indices, data, (r1 - r0, K)))
             del out, stats, Xb

@@ -118,8 +118,8 @@ def test_float64_output_matches_oracle_to_1e11():
         layout = build_layout(var, window, step)
         with DevicePlan(layout, dev) as plan:
             plan.set_reference(torch.from_numpy(ref).to(dev))
-            tmp, stats = plan.smooth(torch.from_numpy(X).to(dev), 3.0, out_dtype=torch.float64)
-            out, _, _, _ = plan.threshold(tmp, stats, 5000, None)
+            tmp = plan.smooth(torch.from_numpy(X).to(dev), 3.0)
+            out, stats = plan.center(tmp, out_dtype=torch.float64)
             got = out.cpu().numpy()
             stats = stats.cpu().numpy()
             tier = plan.tier
@@ -192,9 +192,10 @@ def test_properties_at_scale():
         sums, counts = plan.colsum(Xd)
         ref = plan.mean_from_sums(sums, counts)
         plan.set_reference(ref)
-        tmp, stats = plan.smooth(Xd, 3.0)
-        pre, _, _, _ = plan.threshold(tmp, stats, chunk, None)
-        out, thr, row_abs, row_nnz = plan.threshold(tmp, stats, chunk, 1.5)
+        tmp = plan.smooth(Xd, 3.0)
+        pre, stats = plan.center(tmp)
+        out = pre.clone()
+        thr, row_abs, row_nnz = plan.threshold(out, stats, chunk, 1.5)
         # (1) every row of the pre-threshold matrix has median 0 (even K: mean of the middle pair)
         med = pre.double().median(dim=1).values  # lower median
         srt = pre.double().sort(dim=1).values
@@ -211,16 +212,14 @@ def test_properties_at_scale():
         np.testing.assert_allclose(row_abs.cpu().numpy(), out.double().abs().sum(dim=1).cpu().numpy(), rtol=1e-12)
         assert torch.equal(row_nnz.long(), (out != 0).sum(dim=1))
         # (4) row-shard invariance: two shards cut at a chunk boundary give the same matrix
-        t1, s1 = plan.smooth(Xd[:5000], 3.0)
-        t2, s2 = plan.smooth(Xd[5000:], 3.0)
-        o1 = plan.threshold(t1, s1, chunk, None)[0]
-        o2 = plan.threshold(t2, s2, chunk, None)[0]
+        o1 = plan.center(plan.smooth(Xd[:5000], 3.0))[0]
+        o2 = plan.center(plan.smooth(Xd[5000:], 3.0))[0]
         assert torch.equal(torch.cat([o1, o2]), pre)
         # (5) CSR input (densify on load) == dense input
         sub = Xd[:3000]
         csr = sub.to_sparse_csr()
-        t3, s3 = plan.smooth((csr.crow_indices().to(torch.int64), csr.col_indices().to(torch.int32), csr.values()), 3.0)
-        assert torch.equal(plan.threshold(t3, s3, chunk, None)[0], pre[:3000])
+        t3 = plan.smooth((csr.crow_indices().to(torch.int64), csr.col_indices().to(torch.int32), csr.values()), 3.0)
+        assert torch.equal(plan.center(t3)[0], pre[:3000])
         # (6) CSR conversion round trip
         indptr, indices, data = plan.to_csr(out, row_nnz)
         back = torch.sparse_csr_tensor(indptr, indices.long(), data, size=out.shape).to_dense()
@@ -231,8 +230,7 @@ def test_properties_at_scale():
     layout_p = build_layout(var_p, 100, 10)
     with DevicePlan(layout_p, dev) as plan_p:
         plan_p.set_reference(ref[:, torch.from_numpy(perm).to(dev)].contiguous())
-        t4, s4 = plan_p.smooth(Xd[:2000][:, torch.from_numpy(perm).to(dev)].contiguous(), 3.0)
-        o4 = plan_p.threshold(t4, s4, chunk, None)[0]
+        o4 = plan_p.center(plan_p.smooth(Xd[:2000][:, torch.from_numpy(perm).to(dev)].contiguous(), 3.0))[0]
     assert torch.equal(o4, pre[:2000])
 
 

@@ -44,13 +44,14 @@ for window in WINDOWS:
         sums, counts = plan.colsum(Xd)
         ref = plan.mean_from_sums(sums, counts)
         plan.set_reference(ref)
-        tmp = torch.empty((N, plan.tmp_width()), dtype=torch.float32, device=dev)
+        tmp = torch.empty((N, plan.tmp_width()), dtype=torch.float64, device=dev)
         out = torch.empty((N, K), dtype=torch.float32, device=dev)
         stats = torch.empty((N, 2), dtype=torch.float64, device=dev)
-        t_sm = timeit(lambda: plan.smooth(Xd, 3.0, tmp=tmp, row_stats=stats))
-        t_th = timeit(lambda: plan.threshold(tmp, stats, 5000, 1.5, out=out))
+        t_sm = timeit(lambda: plan.smooth(Xd, 3.0, tmp=tmp))
+        t_ce = timeit(lambda: plan.center(tmp, out=out, row_stats=stats))
+        t_th = timeit(lambda: plan.threshold(out, stats, 5000, 1.5))
         by = N * (4 * G + 4 * K)
         print(json.dumps(dict(window=window, N=N, K=K, launch=info,
               colsum_ms=t_cs, colsum_GBs=N*G*4/t_cs[0]/1e6,
               smooth_ms=t_sm, smooth_GBs=by/t_sm[0]/1e6, smooth_frac=by/t_sm[0]/1e6/peak, cells_per_s=N/t_sm[0]*1e3,
-              thr_ms=t_th, thr_GBs=2*N*K*4/t_th[0]/1e6)))
+              center_ms=t_ce, center_GBs=N*(plan.tmp_width()*8+K*4)/t_ce[0]/1e6, thr_ms=t_th, thr_GBs=2*N*K*4/t_th[0]/1e6)))

@@ -26,9 +26,8 @@ t = buf.cpu().numpy().astype(np.float64)
 rows = slice(4, min(R, N // grid - 2))   # steady state
 T = t[:, rows, :]
 def d(a, b): x = (T[..., b] - T[..., a]).ravel(); x = x[(T[..., a].ravel() > 0) & (T[..., b].ravel() > 0)]; return float(np.median(x)), float(np.mean(x))
-names = {(0,1): "wait row (mbarrier)", (1,2): "own phase-2 blocks", (2,3): "wait BAR_A", (3,13): "TMA issue (tid 0)", (13,15): "phase 3 FMA loops + sums",
-         (15,4): "warp reduce of sums", (4,5): "BAR_B + totals", (5,8): "median: heuristics + keys", (8,14): "median: pass-1 count+redux", (14,9): "median: pass-1 barrier",
-         (9,10): "median: decision(s) + later passes", (10,11): "median: candidate push + barrier", (11,12): "median: rank + barrier", (12,6): "median: return", (6,7): "write-out", (0,7): "whole row"}
+names = {(0,1): "wait row (mbarrier)", (1,2): "own phase-2 blocks", (2,3): "wait BAR_A", (3,13): "after BAR_A", (13,15): "phase 3 FMA loops",
+         (15,4): "tile-order stores", (4,7): "BAR_B", (0,7): "whole row"}
 period = np.diff(t[:, 4:rows.stop, 0], axis=1).ravel()
 print(json.dumps(dict(N=N, window=window, grid=grid, period_median=float(np.median(period)), period_mean=float(period.mean()))))
 for k, v in names.items():
