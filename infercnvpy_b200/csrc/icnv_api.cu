@@ -427,7 +427,7 @@ int icnv_plan_tmp_width(const icnv_plan* plan, int64_t* ld_tmp) {
     int rc = choose(*plan, plan->c64, &ch);
     if (rc) return rc;
     const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
-    *ld_tmp = (int64_t)((n_tasks + 31) / 32) * 32 * LOUT;
+    *ld_tmp = (int64_t)((n_tasks + 31) / 32) * (32 * LOUT + 1);  // values + one float2 of moments per tile
     return ICNV_OK;
 }
 int icnv_plan_kernel_tier(const icnv_plan* plan) {
@@ -544,7 +544,7 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
     if (rc) return rc;
     {
         const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
-        if (ldo < (int64_t)((n_tasks + 31) / 32) * 32 * LOUT) {
+        if (ldo < (int64_t)((n_tasks + 31) / 32) * (32 * LOUT + 1)) {
             set_error("smooth: intermediate pitch smaller than icnv_plan_tmp_width");
             return ICNV_EINVAL;
         }
@@ -639,6 +639,10 @@ int icnv_center_rows(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t
     if (rc) return rc;
     const Task* tasks = ch.tier < 2 ? plan->tasks_g.ptr : plan->tasks_d.ptr;
     const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+    if (ld_tmp < (int64_t)((n_tasks + 31) / 32) * (32 * LOUT + 1)) {
+        set_error("icnv_center_rows: intermediate pitch smaller than icnv_plan_tmp_width");
+        return ICNV_EINVAL;
+    }
     return aux_center_rows(tmp, n_rows, ld_tmp, tasks, n_tasks, (int)plan->K, out, out_is_f64 != 0, ldo, row_stats, (cudaStream_t)stream);
 }
 

@@ -210,15 +210,16 @@ __global__ void __launch_bounds__(256) chunk_threshold_kernel(const double* __re
 
 // Step 4: exact row median + centring (/root/reference/src/infercnvpy/tl/_infercnv.py:442) and the row moments
 // that feed the per-chunk std of :450.  Input: the smoothing kernel's fp64 rows in warp-tile order (value i of task t
-// at (t/32)*32*LOUT + i*32 + t%32).  One WARP per row, no block-level synchronisation: an exact selection is a long
-// dependent chain (keys, counting passes, candidate ranking), and with one row per warp thousands of independent
-// chains are in flight per GPU.  RES = the row lives in registers (<= NT_C tiles of 32 tasks); otherwise every pass
-// re-reads it (L1/L2 hits).
+// at (t/32)*32*LOUT + i*32 + t%32, unused slots = +inf) followed by one float2 (sum, sum of squares) per tile.
+// One WARP per row, no block-level synchronisation: an exact selection is a long dependent chain (keys, counting
+// passes, candidate ranking), and with one row per warp ~3500 independent chains are in flight per GPU.
 //
-// Selection: 32-bit order-preserving keys scaled to mean +- 1.02 sigma (the median is always inside), 8-bin counting
-// passes (packed byte counters, REDUX), then <= 32 candidates are ranked exactly in fp64 (np.median: mean of the two
-// middle values for even K).  Middle ranks on both sides of a bin boundary and > 32 values on one key (ties) have
-// their own exact paths.
+// Selection: the row is read once from HBM and turned into 32-bit order-preserving keys scaled to mean +- 1.02 sigma
+// (from the tile moments; the median is always inside; +inf saturates to the top key), kept in the warp's shared
+// memory.  8-bin counting passes over the keys (packed byte counters, REDUX), then the <= 32 candidates are re-read
+// (L2) and ranked exactly in fp64 (np.median: mean of the two middle values for even K).  Middle ranks on both sides
+// of a bin boundary and > 32 values on one key (ties) have their own exact paths.  The centring sweep reads the row a
+// second time — it was fetched with an evict-last policy a few microseconds earlier, so this is L2 traffic.
 __device__ __forceinline__ double warp_sum_dd(double x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -228,308 +229,88 @@ __device__ __forceinline__ unsigned long long ordered_bits64(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
-
-template <typename TO>
-__global__ void __launch_bounds__(128) center_rows_kernel(const double* __restrict__ tmp, int64_t n_rows, int64_t ld,
-                                                          const Task* __restrict__ tasks, int n_tasks, int K,
-                                                          TO* __restrict__ out, int64_t ldo, double* __restrict__ row_stats) {
-    // per warp: the row (tile order, fp64), the candidate list, the natural-order output slab of one tile
-    extern __shared__ __align__(16) unsigned char cr_smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int n_tiles = (n_tasks + 31) >> 5;
-    const size_t row_elems = (size_t)n_tiles * (32 * LOUT);
-    const size_t per_warp = row_elems * 8 + CAND_CAP * 8 + (size_t)(32 * LOUT) * sizeof(TO);
-    double* vrow = reinterpret_cast<double*>(cr_smem + wib * ((per_warp + 15) / 16 * 16));
-    double* cand_w = vrow + row_elems;
-    TO* stage_w = reinterpret_cast<TO*>(cand_w + CAND_CAP);
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    auto tile_geom = [&](int t, int& c0, int& cn) {
-        const int ti = t * 32 + lane;
-        c0 = 0;
-        cn = 0;
-        if (ti < n_tasks) {
-            const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks) + ti);
-            c0 = tk.y;
-            cn = (tk.w & 0xFF) ? 1 : tk.z;
-        }
-    };
-    const int r1 = (K - 1) >> 1, r2 = K >> 1;
-
-    for (int64_t row = warp; row < n_rows; row += n_warps) {
-        // stage the row verbatim (coalesced 256-byte lines); each lane only ever reads back its own column
-        {
-            const double* src = tmp + row * ld;
-            __syncwarp();
-            for (size_t e = lane; e < row_elems; e += 32) vrow[e] = src[e];
-            __syncwarp();
-        }
-        const double* rowp = vrow + lane;
-// BODY sees `x` = one valid value of this lane
-#define EACH_VALUE(BODY)                                                      \
-    for (int t_ = 0; t_ < n_tiles; ++t_) {                                    \
-        int c0_, cn_;                                                         \
-        tile_geom(t_, c0_, cn_);                                              \
-        for (int i_ = 0; i_ < cn_; ++i_) {                                    \
-            const double x = rowp[(size_t)t_ * (32 * LOUT) + i_ * 32];        \
-            BODY                                                              \
-        }                                                                     \
-    }
-        // ---- location / scale in fp32 (steers the bracket only)
-        float f1 = 0.f, f2 = 0.f;
-        EACH_VALUE({
-            const float xf = (float)x;
-            f1 += xf;
-            f2 = fmaf(xf, xf, f2);
-        })
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            f1 += __shfl_xor_sync(0xffffffffu, f1, o);
-            f2 += __shfl_xor_sync(0xffffffffu, f2, o);
-        }
-        const float invK = 1.f / (float)K;
-        const float mean = f1 * invK;
-        const float var = fmaxf(f2 * invK - mean * mean, 0.f);
-        const float half = fmaxf(1.02f * sqrtf(var) + 1e-6f * fabsf(mean), 1e-20f);
-        const double kbase = (double)(mean - half);
-        const double kscale = (double)(2147483648.f / half);
-#define KEY_OF(xx) __double2uint_rd(((xx)-kbase) * kscale)
-
-        uint32_t klo = 0, ksplit = 0;
-        int shift = 29, below = 0, state = -1;
-        while (state < 0) {
-            uint32_t wl = 0, wh = 0;  // byte counters: bins 0-3 / 4-7 (a lane holds < 256 values)
-            EACH_VALUE({
-                const uint32_t b = (KEY_OF(x) - klo) >> shift;
-                const uint32_t inc = 1u << ((b & 3u) << 3);
-                wl += b < 4u ? inc : 0u;
-                wh += (b >= 4u && b < 8u) ? inc : 0u;
-            })
-            uint32_t w0 = (wl & 0xFFu) | ((wl & 0xFF00u) << 8), w1 = ((wl >> 16) & 0xFFu) | ((wl >> 8) & 0xFF0000u);
-            uint32_t w2 = (wh & 0xFFu) | ((wh & 0xFF00u) << 8), w3 = ((wh >> 16) & 0xFFu) | ((wh >> 8) & 0xFF0000u);
-            w0 = __reduce_add_sync(0xffffffffu, w0);
-            w1 = __reduce_add_sync(0xffffffffu, w1);
-            w2 = __reduce_add_sync(0xffffffffu, w2);
-            w3 = __reduce_add_sync(0xffffffffu, w3);
-            int cum = below, b1 = -1, b2 = -1, below1 = below, n_in = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const uint32_t word = b < 2 ? w0 : (b < 4 ? w1 : (b < 6 ? w2 : w3));
-                const int cb = (b & 1) ? (int)(word >> 16) : (int)(word & 0xFFFFu);
-                const int nc = cum + cb;
-                if (b1 < 0 && nc > r1) {
-                    b1 = b;
-                    below1 = cum;
-                    n_in = cb;
-                }
-                if (b2 < 0 && nc > r2) b2 = b;
-                cum = nc;
-            }
-            if (b1 < 0 || b2 < 0) {  // only for non-finite input: exact path over everything
-                state = 3;
-                klo = 0;
-                shift = 32;
-                below = 0;
-            } else if (b1 != b2) {
-                state = 2;
-                ksplit = klo + ((uint32_t)b2 << shift);
-            } else {
-                klo += (uint32_t)b1 << shift;
-                below = below1;
-                if (n_in <= CAND_CAP)
-                    state = 1;
-                else if (shift == 0)
-                    state = 3;
-                else
-                    shift = shift >= 3 ? shift - 3 : 0;
-            }
-        }
-
-        double m;
-        if (state == 1) {
-            // compact the <= CAND_CAP values of the final key range into shared memory, rank them exactly
-            int mine_n = 0;
-            EACH_VALUE({ mine_n += ((KEY_OF(x) - klo) >> shift) == 0u; })
-            int incl = mine_n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int n = __shfl_sync(0xffffffffu, incl, 31);
-            int slot = incl - mine_n;
-            __syncwarp();
-            EACH_VALUE({
-                if (((KEY_OF(x) - klo) >> shift) == 0u) cand_w[slot++] = x;
-            })
-            __syncwarp();
-            const double mine = lane < n ? cand_w[lane] : INFINITY;
-            int rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const double o = cand_w[j];
-                rank += (o < mine) || (o == mine && j < lane);
-            }
-            const unsigned q1 = __ballot_sync(0xffffffffu, lane < n && rank == r1 - below);
-            const unsigned q2 = __ballot_sync(0xffffffffu, lane < n && rank == r2 - below);
-            const double lo = __shfl_sync(0xffffffffu, mine, (__ffs(q1) - 1) & 31);
-            const double hi = __shfl_sync(0xffffffffu, mine, (__ffs(q2) - 1) & 31);
-            m = (lo + hi) / 2.0;
-        } else if (state == 2) {
-            double lo = -INFINITY, hi = INFINITY;
-            EACH_VALUE({
-                if (KEY_OF(x) < ksplit)
-                    lo = fmax(lo, x);
-                else
-                    hi = fmin(hi, x);
-            })
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = fmin(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            }
-            m = (lo + hi) / 2.0;
-        } else {
-            // > CAND_CAP values on one key (ties / degenerate rows): exact bitwise select on the ordered fp64 pattern
-            double res[2] = {0.0, 0.0};
-            for (int which = 0; which < 2; ++which) {
-                if (which == 1 && r2 == r1) {
-                    res[1] = res[0];
-                    break;
-                }
-                int rr = (which == 0 ? r1 : r2) - below;
-                unsigned long long prefix = 0;
-                for (int bit = 63; bit >= 0; --bit) {
-                    int local = 0;
-                    EACH_VALUE({
-                        const bool in_set = shift >= 32 ? true : (((KEY_OF(x) - klo) >> shift) == 0u);
-                        const unsigned long long ob = ordered_bits64(x);
-                        const bool same = bit == 63 ? true : ((ob >> (bit + 1)) == (prefix >> (bit + 1)));
-                        local += in_set && same && !((ob >> bit) & 1ull);
-                    })
-                    const int zeros = __reduce_add_sync(0xffffffffu, local);
-                    if (rr >= zeros) {
-                        rr -= zeros;
-                        prefix |= 1ull << bit;
-                    }
-                }
-                const unsigned long long bb = (prefix >> 63) ? (prefix & 0x7FFFFFFFFFFFFFFFull) : ~prefix;
-                res[which] = __longlong_as_double((long long)bb);
-            }
-            m = (res[0] + res[1]) / 2.0;
-        }
-#undef KEY_OF
-
-        // ---- centre, row moments, natural-order write through a per-warp slab (one tile = one contiguous column range)
-        double s = 0.0, ss = 0.0;
-        for (int t = 0; t < n_tiles; ++t) {
-            int c0, cn;
-            tile_geom(t, c0, cn);
-            const int base = __shfl_sync(0xffffffffu, c0, 0);
-            const int end = __reduce_max_sync(0xffffffffu, c0 + cn);
-            for (int i = 0; i < cn; ++i) {
-                const double x = rowp[(size_t)t * (32 * LOUT) + i * 32] - m;
-                s += x;
-                ss = fma(x, x, ss);
-                stage_w[c0 - base + i] = (TO)x;
-            }
-            __syncwarp();
-            TO* dst = out + row * ldo + base;
-            for (int k = lane; k < end - base; k += 32) dst[k] = stage_w[k];
-            __syncwarp();
-        }
-        s = warp_sum_dd(s);
-        ss = warp_sum_dd(ss);
-        if (lane == 0) {
-            row_stats[2 * row] = s;
-            row_stats[2 * row + 1] = ss;
-        }
-#undef EACH_VALUE
-    }
+__device__ __forceinline__ double ldg_keep_f64(const double* p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
 }
 
-// Fast variant for rows of at most NT_C tiles (the bench shapes have 7): the 32-bit keys and the per-tile task geometry
-// live in registers (compile-time indexed, fully unrolled sweeps); the fp64 values stay in the per-warp shared-memory
-// copy and are only touched for the moments, the <= 32 candidates and the final centring.
-template <typename TO, int NT_C>
-__global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __restrict__ tmp, int64_t n_rows, int64_t ld,
-                                                               const Task* __restrict__ tasks, int n_tasks, int K,
-                                                               TO* __restrict__ out, int64_t ldo, double* __restrict__ row_stats) {
+constexpr int CENTER_WARPS = 8;
+constexpr int TILE_V = 32 * LOUT;
+
+template <typename TO>
+__global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const double* __restrict__ tmp, int64_t n_rows, int64_t ld,
+                                                                        const Task* __restrict__ tasks, int n_tasks, int K,
+                                                                        TO* __restrict__ out, int64_t ldo,
+                                                                        double* __restrict__ row_stats) {
+    // CTA: (column, count) of every task; per warp: the row's keys, the candidate list, one tile of natural-order output
     extern __shared__ __align__(16) unsigned char cr_smem[];
-    constexpr int NV = NT_C * LOUT;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n_tiles = (n_tasks + 31) >> 5;
-    const size_t row_elems = (size_t)n_tiles * (32 * LOUT);
-    const size_t per_warp = row_elems * 8 + CAND_CAP * 8 + (size_t)(32 * LOUT) * sizeof(TO);
-    double* vrow = reinterpret_cast<double*>(cr_smem + wib * ((per_warp + 15) / 16 * 16));
-    double* cand_w = vrow + row_elems;
+    const int row_elems = n_tiles * TILE_V;
+    int2* geom = reinterpret_cast<int2*>(cr_smem);
+    const size_t per_warp = ((size_t)row_elems * 4 + CAND_CAP * 8 + (size_t)TILE_V * sizeof(TO) + 15) / 16 * 16;
+    unsigned char* wbase = cr_smem + (((size_t)n_tiles * 32 * sizeof(int2) + 15) / 16 * 16) + wib * per_warp;
+    double* cand_w = reinterpret_cast<double*>(wbase);
     TO* stage_w = reinterpret_cast<TO*>(cand_w + CAND_CAP);
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int col0[NT_C], cnt[NT_C], tbase[NT_C], tend[NT_C];
-#pragma unroll
-    for (int t = 0; t < NT_C; ++t) {
-        const int ti = t * 32 + lane;
-        col0[t] = 0;
-        cnt[t] = 0;
+    uint32_t* keys_w = reinterpret_cast<uint32_t*>(stage_w + TILE_V) + lane;
+    for (int ti = threadIdx.x; ti < n_tiles * 32; ti += blockDim.x) {
+        int2 g = make_int2(0, 0);
         if (ti < n_tasks) {
             const int4 tk = __ldg(reinterpret_cast<const int4*>(tasks) + ti);
-            col0[t] = tk.y;
-            cnt[t] = (tk.w & 0xFF) ? 1 : tk.z;
+            g = make_int2(tk.y, (tk.w & 0xFF) ? 1 : tk.z);
         }
-        tbase[t] = __shfl_sync(0xffffffffu, col0[t], 0);
-        tend[t] = __reduce_max_sync(0xffffffffu, col0[t] + cnt[t]);
+        geom[ti] = g;
     }
+    __syncthreads();
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    const int64_t warp = (int64_t)blockIdx.x * CENTER_WARPS + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * CENTER_WARPS;
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
-    const double* rowp = vrow + lane;
+    const float invK = 1.f / (float)K;
 
     for (int64_t row = warp; row < n_rows; row += n_warps) {
-        {
-            const double2* src = reinterpret_cast<const double2*>(tmp + row * ld);
-            double2* dst = reinterpret_cast<double2*>(vrow);
-            __syncwarp();
-            for (int e = lane; e < (int)(row_elems >> 1); e += 32) dst[e] = src[e];
-            __syncwarp();
-        }
+        const double* src = tmp + row * ld + lane;
         // ---- location / scale (fp32, steers the bracket only)
         float f1 = 0.f, f2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < NT_C; ++t)
-#pragma unroll
-            for (int i = 0; i < LOUT; ++i)
-                if (i < cnt[t]) {
-                    const float xf = (float)rowp[t * (32 * LOUT) + i * 32];
-                    f1 += xf;
-                    f2 = fmaf(xf, xf, f2);
-                }
+        if (lane < n_tiles) {
+            const float2 mo = __ldg(reinterpret_cast<const float2*>(tmp + row * ld + row_elems) + lane);
+            f1 = mo.x;
+            f2 = mo.y;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             f1 += __shfl_xor_sync(0xffffffffu, f1, o);
             f2 += __shfl_xor_sync(0xffffffffu, f2, o);
         }
-        const float invK = 1.f / (float)K;
         const float mean = f1 * invK;
         const float var = fmaxf(f2 * invK - mean * mean, 0.f);
         const float half = fmaxf(1.02f * sqrtf(var) + 1e-6f * fabsf(mean), 1e-20f);
         const double kbase = (double)(mean - half);
         const double kscale = (double)(2147483648.f / half);
-        uint32_t key[NV];
+        // ---- keys (saturating: below the bracket -> 0, above / unused slot -> 0xFFFFFFFF)
+        for (int t = 0; t < n_tiles; ++t) {
+            double x[LOUT];
 #pragma unroll
-        for (int t = 0; t < NT_C; ++t)
+            for (int i = 0; i < LOUT; ++i) x[i] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
 #pragma unroll
-            for (int i = 0; i < LOUT; ++i)
-                key[t * LOUT + i] = (i < cnt[t]) ? __double2uint_rd((rowp[t * (32 * LOUT) + i * 32] - kbase) * kscale) : 0xFFFFFFFFu;
-        // unused slots carry the top key: they sort last and never reach the middle ranks
+            for (int i = 0; i < LOUT; ++i) keys_w[t * TILE_V + i * 32] = __double2uint_rd((x[i] - kbase) * kscale);
+        }
+        // every lane only ever reads back its own keys: no warp sync needed
 
         uint32_t klo = 0, ksplit = 0;
         int shift = 29, below = 0, state = -1;
         while (state < 0) {
             uint32_t wl = 0, wh = 0;
+            for (int t = 0; t < n_tiles; ++t) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                const uint32_t b = (key[k] - klo) >> shift;
-                const uint32_t inc = 1u << ((b & 3u) << 3);
-                wl += b < 4u ? inc : 0u;
-                wh += (b >= 4u && b < 8u) ? inc : 0u;
+                for (int i = 0; i < LOUT; ++i) {
+                    const uint32_t b = (keys_w[t * TILE_V + i * 32] - klo) >> shift;
+                    const uint32_t inc = 1u << ((b & 3u) << 3);
+                    wl += b < 4u ? inc : 0u;
+                    wh += (b >= 4u && b < 8u) ? inc : 0u;
+                }
             }
             uint32_t w0 = (wl & 0xFFu) | ((wl & 0xFF00u) << 8), w1 = ((wl >> 16) & 0xFFu) | ((wl >> 8) & 0xFF0000u);
             uint32_t w2 = (wh & 0xFFu) | ((wh & 0xFF00u) << 8), w3 = ((wh >> 16) & 0xFFu) | ((wh >> 8) & 0xFF0000u);
@@ -552,6 +333,7 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
                 cum = nc;
             }
             if (b1 < 0 || b2 < 0) {
+                // cannot happen with a consistent bracket; fall back to the exact bitwise selection over the row
                 state = 3;
                 klo = 0;
                 shift = 32;
@@ -574,8 +356,9 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
         double m;
         if (state == 1) {
             int mine_n = 0;
+            for (int t = 0; t < n_tiles; ++t)
 #pragma unroll
-            for (int k = 0; k < NV; ++k) mine_n += ((key[k] - klo) >> shift) == 0u;
+                for (int i = 0; i < LOUT; ++i) mine_n += ((keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u;
             int incl = mine_n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -585,11 +368,11 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
             const int n = __shfl_sync(0xffffffffu, incl, 31);
             int slot = incl - mine_n;
             __syncwarp();
+            if (mine_n)
+                for (int t = 0; t < n_tiles; ++t)
 #pragma unroll
-            for (int t = 0; t < NT_C; ++t)
-#pragma unroll
-                for (int i = 0; i < LOUT; ++i)
-                    if (((key[t * LOUT + i] - klo) >> shift) == 0u) cand_w[slot++] = rowp[t * (32 * LOUT) + i * 32];
+                    for (int i = 0; i < LOUT; ++i)
+                        if (((keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u) cand_w[slot++] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
             __syncwarp();
             const double mine = lane < n ? cand_w[lane] : INFINITY;
             int rank = 0;
@@ -603,18 +386,17 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
             const double hi = __shfl_sync(0xffffffffu, mine, (__ffs(q2) - 1) & 31);
             m = (lo + hi) / 2.0;
         } else if (state == 2) {
+            // the two middle ranks sit on either side of a bin boundary: largest value below, smallest above
             double lo = -INFINITY, hi = INFINITY;
+            for (int t = 0; t < n_tiles; ++t)
 #pragma unroll
-            for (int t = 0; t < NT_C; ++t)
-#pragma unroll
-                for (int i = 0; i < LOUT; ++i)
-                    if (i < cnt[t]) {
-                        const double x = rowp[t * (32 * LOUT) + i * 32];
-                        if (key[t * LOUT + i] < ksplit)
-                            lo = fmax(lo, x);
-                        else
-                            hi = fmin(hi, x);
-                    }
+                for (int i = 0; i < LOUT; ++i) {
+                    const double x = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
+                    if (keys_w[t * TILE_V + i * 32] < ksplit)
+                        lo = fmax(lo, x);
+                    else
+                        hi = fmin(hi, x);
+                }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -622,6 +404,7 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
             }
             m = (lo + hi) / 2.0;
         } else {
+            // ties beyond the candidate capacity: exact bitwise selection on the order-preserving 64-bit pattern
             double res[2] = {0.0, 0.0};
             for (int which = 0; which < 2; ++which) {
                 if (which == 1 && r2 == r1) {
@@ -632,16 +415,17 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
                 unsigned long long prefix = 0;
                 for (int bit = 63; bit >= 0; --bit) {
                     int local = 0;
-#pragma unroll
-                    for (int t = 0; t < NT_C; ++t)
+                    for (int t = 0; t < n_tiles; ++t) {
+                        const int cnt = geom[t * 32 + lane].y;
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i)
-                            if (i < cnt[t]) {
-                                const bool in_set = shift >= 32 ? true : (((key[t * LOUT + i] - klo) >> shift) == 0u);
-                                const unsigned long long ob = ordered_bits64(rowp[t * (32 * LOUT) + i * 32]);
+                            if (i < cnt) {
+                                const bool in_set = shift >= 32 ? true : (((keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u);
+                                const unsigned long long ob = ordered_bits64(ldg_keep_f64(src + t * TILE_V + i * 32, pol));
                                 const bool same = bit == 63 ? true : ((ob >> (bit + 1)) == (prefix >> (bit + 1)));
                                 local += in_set && same && !((ob >> bit) & 1ull);
                             }
+                    }
                     const int zeros = __reduce_add_sync(0xffffffffu, local);
                     if (rr >= zeros) {
                         rr -= zeros;
@@ -656,22 +440,25 @@ __global__ void __launch_bounds__(128) center_rows_fast_kernel(const double* __r
 
         // ---- centre, row moments, natural-order write
         double s = 0.0, ss = 0.0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int2 g = geom[t * 32 + lane];
+            const int tb = __shfl_sync(0xffffffffu, g.x, 0);
+            const int te = __reduce_max_sync(0xffffffffu, g.x + g.y);
+            double x[LOUT];
 #pragma unroll
-        for (int t = 0; t < NT_C; ++t) {
-            if (t < n_tiles) {
+            for (int i = 0; i < LOUT; ++i) x[i] = (i < g.y) ? ldg_keep_f64(src + t * TILE_V + i * 32, pol) : 0.0;
 #pragma unroll
-                for (int i = 0; i < LOUT; ++i)
-                    if (i < cnt[t]) {
-                        const double x = rowp[t * (32 * LOUT) + i * 32] - m;
-                        s += x;
-                        ss = fma(x, x, ss);
-                        stage_w[col0[t] - tbase[t] + i] = (TO)x;
-                    }
-                __syncwarp();
-                TO* dst = out + row * ldo + tbase[t];
-                for (int k = lane; k < tend[t] - tbase[t]; k += 32) dst[k] = stage_w[k];
-                __syncwarp();
-            }
+            for (int i = 0; i < LOUT; ++i)
+                if (i < g.y) {
+                    const double c = x[i] - m;
+                    s += c;
+                    ss = fma(c, c, ss);
+                    stage_w[g.x - tb + i] = (TO)c;
+                }
+            __syncwarp();
+            TO* dst = out + row * ldo + tb;
+            for (int k = lane; k < te - tb; k += 32) __stcs(dst + k, stage_w[k]);
+            __syncwarp();
         }
         s = warp_sum_dd(s);
         ss = warp_sum_dd(ss);
@@ -891,26 +678,23 @@ int aux_center_rows(const double* tmp, int64_t n_rows, int64_t ld, const Task* t
         set_error("icnv_center_rows: more than 28 tiles of tasks per row (byte counters would overflow)");
         return -3;
     }
-    const size_t per_warp = (((size_t)n_tiles * (32 * LOUT) * 8 + CAND_CAP * 8 + (size_t)(32 * LOUT) * (f64 ? 8 : 4)) + 15) / 16 * 16;
-    int wpc = (int)(100000 / per_warp);  // two CTAs per SM
-    if (wpc > 4) wpc = 4;
-    if (wpc < 1) wpc = 1;
-    const size_t smem = per_warp * wpc;
-    const int64_t want = (n_rows + wpc - 1) / wpc;
-    const int grid = (int)(want < (int64_t)(148 * 16) ? want : (int64_t)(148 * 16));
-#define ICNV_CENTER(KERNEL, TO_)                                                                          \
-    do {                                                                                                  \
-        ICNV_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        KERNEL<<<grid, 32 * wpc, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (TO_*)out, ldo, row_stats); \
-    } while (0)
-    if (n_tiles <= 4) {
-        if (f64) ICNV_CENTER((center_rows_fast_kernel<double, 4>), double); else ICNV_CENTER((center_rows_fast_kernel<float, 4>), float);
-    } else if (n_tiles <= 7) {
-        if (f64) ICNV_CENTER((center_rows_fast_kernel<double, 7>), double); else ICNV_CENTER((center_rows_fast_kernel<float, 7>), float);
+    const size_t per_warp = ((size_t)n_tiles * TILE_V * 4 + CAND_CAP * 8 + (size_t)TILE_V * (f64 ? 8 : 4) + 15) / 16 * 16;
+    const size_t smem = ((size_t)n_tiles * 32 * sizeof(int2) + 15) / 16 * 16 + per_warp * CENTER_WARPS;
+    int dev = 0, n_sm = 148;
+    ICNV_CUDA(cudaGetDevice(&dev));
+    ICNV_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;  // 24 warps per SM
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (n_rows + CENTER_WARPS - 1) / CENTER_WARPS;
+    const int grid = (int)(want < (int64_t)n_sm * per_sm ? want : (int64_t)n_sm * per_sm);
+    if (f64) {
+        ICNV_CUDA(cudaFuncSetAttribute(center_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        center_rows_kernel<double><<<grid, 32 * CENTER_WARPS, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (double*)out, ldo, row_stats);
     } else {
-        if (f64) ICNV_CENTER(center_rows_kernel<double>, double); else ICNV_CENTER(center_rows_kernel<float>, float);
+        ICNV_CUDA(cudaFuncSetAttribute(center_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        center_rows_kernel<float><<<grid, 32 * CENTER_WARPS, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (float*)out, ldo, row_stats);
     }
-#undef ICNV_CENTER
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }

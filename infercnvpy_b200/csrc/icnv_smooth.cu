@@ -383,7 +383,24 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
             // the 32 lanes of a warp write 32 consecutive values per instruction (256-byte lines)
             const int ti = tid + tt * NT;
             if (ti < ((p.n_tasks + 31) & ~31)) {
-                double* o = reinterpret_cast<double*>(p.out) + (size_t)row * p.ldo + (size_t)(ti >> 5) * (32 * LOUT) + (ti & 31);
+                // tile moments behind the values: they steer the median bracket of center_rows (fp32 is plenty)
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < LOUT; ++i)
+                    if (i < nv[tt]) {
+                        s1 += v[tt * LOUT + i];
+                        s2 = fma(v[tt * LOUT + i], v[tt * LOUT + i], s2);
+                    }
+                float f1 = (float)s1, f2 = (float)s2;
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1) {
+                    f1 += __shfl_xor_sync(0xffffffffu, f1, sh);
+                    f2 += __shfl_xor_sync(0xffffffffu, f2, sh);
+                }
+                double* orow = reinterpret_cast<double*>(p.out) + (size_t)row * p.ldo;
+                if (lane == 0)
+                    reinterpret_cast<float2*>(orow + (size_t)((p.n_tasks + 31) >> 5) * (32 * LOUT))[ti >> 5] = make_float2(f1, f2);
+                double* o = orow + (size_t)(ti >> 5) * (32 * LOUT) + (ti & 31);
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i) o[i * 32] = v[tt * LOUT + i];
             }
