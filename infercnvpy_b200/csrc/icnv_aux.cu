@@ -211,15 +211,16 @@ __global__ void __launch_bounds__(256) chunk_threshold_kernel(const double* __re
 // Step 4: exact row median + centring (/root/reference/src/infercnvpy/tl/_infercnv.py:442) and the row moments
 // that feed the per-chunk std of :450.  Input: the smoothing kernel's fp64 rows in warp-tile order (value i of task t
 // at (t/32)*32*LOUT + i*32 + t%32, unused slots = +inf) followed by one float2 (sum, sum of squares) per tile.
-// One WARP per row, no block-level synchronisation: an exact selection is a long dependent chain (keys, counting
-// passes, candidate ranking), and with one row per warp ~3500 independent chains are in flight per GPU.
+// One WARP per row, no block-level synchronisation: an exact selection is a long dependent chain, and with one row
+// per warp ~3500 independent chains are in flight per GPU.
 //
-// Selection: the row is read once from HBM and turned into 32-bit order-preserving keys scaled to mean +- 1.02 sigma
+// Selection: the row is read once from HBM and turned into 16-bit order-preserving keys scaled to mean +- 1.02 sigma
 // (from the tile moments; the median is always inside; +inf saturates to the top key), kept in the warp's shared
-// memory.  8-bin counting passes over the keys (packed byte counters, REDUX), then the <= 32 candidates are re-read
-// (L2) and ranked exactly in fp64 (np.median: mean of the two middle values for even K).  Middle ranks on both sides
-// of a bin boundary and > 32 values on one key (ties) have their own exact paths.  The centring sweep reads the row a
-// second time — it was fetched with an evict-last policy a few microseconds earlier, so this is L2 traffic.
+// memory.  The same sweep fills a 64-bin histogram (per-lane byte counters, so no atomics); the bin holding the two
+// middle ranks has ~1 % of the row, i.e. usually <= 32 candidates, which are re-read (L2) and ranked exactly in fp64
+// (np.median: mean of the two middle values for even K).  Crowded bins are refined (64 sub-bins per level); ties
+// beyond that fall back to an exact bitwise selection.  The centring sweep reads the row a second time — it was
+// fetched with an evict-last policy a few microseconds earlier, so this is L2 traffic.
 __device__ __forceinline__ double warp_sum_dd(double x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -234,26 +235,43 @@ __device__ __forceinline__ double ldg_keep_f64(const double* p, uint64_t pol) {
     asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
+__device__ __forceinline__ uint16_t key16_sat(double v) {  // floor, saturating to [0, 65535]
+    uint16_t k;
+    asm("cvt.rmi.u16.f64 %0, %1;" : "=h"(k) : "d"(v));
+    return k;
+}
 
 constexpr int CENTER_WARPS = 8;
 constexpr int TILE_V = 32 * LOUT;
+constexpr int HIST_BINS = 64;
+
+struct CenterSmem {  // per-warp carve-up, shared by the kernel and its launcher
+    size_t key_bytes, per_warp, geom_bytes, total;
+    __host__ __device__ CenterSmem(int n_tiles, int warps) {
+        // the output tile (<= 8 bytes per value) is staged over the keys, which are dead by then
+        key_bytes = (size_t)n_tiles * TILE_V * 2 > (size_t)TILE_V * 8 ? (size_t)n_tiles * TILE_V * 2 : (size_t)TILE_V * 8;
+        per_warp = (CAND_CAP * 8 + HIST_BINS * 32 + key_bytes + 15) / 16 * 16;
+        geom_bytes = ((size_t)n_tiles * 32 * sizeof(int2) + 15) / 16 * 16;
+        total = geom_bytes + per_warp * warps;
+    }
+};
 
 template <typename TO>
-__global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const double* __restrict__ tmp, int64_t n_rows, int64_t ld,
-                                                                        const Task* __restrict__ tasks, int n_tasks, int K,
-                                                                        TO* __restrict__ out, int64_t ldo,
-                                                                        double* __restrict__ row_stats) {
-    // CTA: (column, count) of every task; per warp: the row's keys, the candidate list, one tile of natural-order output
+__global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const double* __restrict__ tmp, int64_t n_rows, int64_t ld,
+                                                                           const Task* __restrict__ tasks, int n_tasks, int K,
+                                                                           TO* __restrict__ out, int64_t ldo,
+                                                                           double* __restrict__ row_stats) {
     extern __shared__ __align__(16) unsigned char cr_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n_tiles = (n_tasks + 31) >> 5;
     const int row_elems = n_tiles * TILE_V;
-    int2* geom = reinterpret_cast<int2*>(cr_smem);
-    const size_t per_warp = ((size_t)row_elems * 4 + CAND_CAP * 8 + (size_t)TILE_V * sizeof(TO) + 15) / 16 * 16;
-    unsigned char* wbase = cr_smem + (((size_t)n_tiles * 32 * sizeof(int2) + 15) / 16 * 16) + wib * per_warp;
+    const CenterSmem lay(n_tiles, CENTER_WARPS);
+    int2* geom = reinterpret_cast<int2*>(cr_smem);  // CTA: (column, count) of every task
+    unsigned char* wbase = cr_smem + lay.geom_bytes + wib * lay.per_warp;
     double* cand_w = reinterpret_cast<double*>(wbase);
-    TO* stage_w = reinterpret_cast<TO*>(cand_w + CAND_CAP);
-    uint32_t* keys_w = reinterpret_cast<uint32_t*>(stage_w + TILE_V) + lane;
+    unsigned char* hist = wbase + CAND_CAP * 8;  // [64 bins][32 lanes] byte counters
+    TO* stage_w = reinterpret_cast<TO*>(hist + HIST_BINS * 32);
+    uint16_t* keys_w = reinterpret_cast<uint16_t*>(hist + HIST_BINS * 32) + lane;
     for (int ti = threadIdx.x; ti < n_tiles * 32; ti += blockDim.x) {
         int2 g = make_int2(0, 0);
         if (ti < n_tasks) {
@@ -269,6 +287,10 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
     const int64_t n_warps = (int64_t)gridDim.x * CENTER_WARPS;
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
     const float invK = 1.f / (float)K;
+    uint4* hist_mine = reinterpret_cast<uint4*>(hist) + lane * 4;  // lane L sums / clears bins 2L and 2L+1 (64 bytes)
+
+#define ICNV_LOAD_TILE(X, T) \
+    _Pragma("unroll") for (int i = 0; i < LOUT; ++i) X[i] = ldg_keep_f64(src + (T) * TILE_V + i * 32, pol)
 
     for (int64_t row = warp; row < n_rows; row += n_warps) {
         const double* src = tmp + row * ld + lane;
@@ -288,77 +310,117 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
         const float var = fmaxf(f2 * invK - mean * mean, 0.f);
         const float half = fmaxf(1.02f * sqrtf(var) + 1e-6f * fabsf(mean), 1e-20f);
         const double kbase = (double)(mean - half);
-        const double kscale = (double)(2147483648.f / half);
-        // ---- keys (saturating: below the bracket -> 0, above / unused slot -> 0xFFFFFFFF)
-        for (int t = 0; t < n_tiles; ++t) {
-            double x[LOUT];
+        const double kscale = (double)(32768.f / half);
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < LOUT; ++i) x[i] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
-#pragma unroll
-            for (int i = 0; i < LOUT; ++i) keys_w[t * TILE_V + i * 32] = __double2uint_rd((x[i] - kbase) * kscale);
-        }
-        // every lane only ever reads back its own keys: no warp sync needed
-
-        uint32_t klo = 0, ksplit = 0;
-        int shift = 29, below = 0, state = -1;
-        while (state < 0) {
-            uint32_t wl = 0, wh = 0;
-            for (int t = 0; t < n_tiles; ++t) {
+        for (int q = 0; q < 4; ++q) hist_mine[q] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        // ---- keys + level-0 histogram; two tiles of loads in flight per lane
+        {
+            double xa[LOUT], xb[LOUT];
+            auto key_tile = [&](const double (&x)[LOUT], int t) {
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i) {
-                    const uint32_t b = (keys_w[t * TILE_V + i * 32] - klo) >> shift;
-                    const uint32_t inc = 1u << ((b & 3u) << 3);
-                    wl += b < 4u ? inc : 0u;
-                    wh += (b >= 4u && b < 8u) ? inc : 0u;
+                    const uint16_t k = key16_sat((x[i] - kbase) * kscale);
+                    keys_w[t * TILE_V + i * 32] = k;
+                    hist[((uint32_t)k >> 10) * 32 + lane] += 1;
+                }
+            };
+            ICNV_LOAD_TILE(xa, 0);
+            for (int t = 0; t < n_tiles; t += 2) {
+                if (t + 1 < n_tiles) ICNV_LOAD_TILE(xb, t + 1);
+                key_tile(xa, t);
+                if (t + 1 < n_tiles) {
+                    if (t + 2 < n_tiles) ICNV_LOAD_TILE(xa, t + 2);
+                    key_tile(xb, t + 1);
                 }
             }
-            uint32_t w0 = (wl & 0xFFu) | ((wl & 0xFF00u) << 8), w1 = ((wl >> 16) & 0xFFu) | ((wl >> 8) & 0xFF0000u);
-            uint32_t w2 = (wh & 0xFFu) | ((wh & 0xFF00u) << 8), w3 = ((wh >> 16) & 0xFFu) | ((wh >> 8) & 0xFF0000u);
-            w0 = __reduce_add_sync(0xffffffffu, w0);
-            w1 = __reduce_add_sync(0xffffffffu, w1);
-            w2 = __reduce_add_sync(0xffffffffu, w2);
-            w3 = __reduce_add_sync(0xffffffffu, w3);
-            int cum = below, b1 = -1, b2 = -1, below1 = below, n_in = 0;
+        }
+
+        uint32_t klo = 0, ksplit = 0;
+        int shift = 10, below = 0, state = -1, b1 = -1, b2 = -1;
+        while (true) {
+            __syncwarp();
+            // bin totals: lane L owns bins 2L, 2L+1
+            uint32_t c0 = 0, c1 = 0;
+            {
+                const uint4 h0 = hist_mine[0], h1 = hist_mine[1], h2 = hist_mine[2], h3 = hist_mine[3];
+                c0 = __dp4a(h0.x, 0x01010101u, c0);
+                c0 = __dp4a(h0.y, 0x01010101u, c0);
+                c0 = __dp4a(h0.z, 0x01010101u, c0);
+                c0 = __dp4a(h0.w, 0x01010101u, c0);
+                c0 = __dp4a(h1.x, 0x01010101u, c0);
+                c0 = __dp4a(h1.y, 0x01010101u, c0);
+                c0 = __dp4a(h1.z, 0x01010101u, c0);
+                c0 = __dp4a(h1.w, 0x01010101u, c0);
+                c1 = __dp4a(h2.x, 0x01010101u, c1);
+                c1 = __dp4a(h2.y, 0x01010101u, c1);
+                c1 = __dp4a(h2.z, 0x01010101u, c1);
+                c1 = __dp4a(h2.w, 0x01010101u, c1);
+                c1 = __dp4a(h3.x, 0x01010101u, c1);
+                c1 = __dp4a(h3.y, 0x01010101u, c1);
+                c1 = __dp4a(h3.z, 0x01010101u, c1);
+                c1 = __dp4a(h3.w, 0x01010101u, c1);
+            }
+            int incl = (int)(c0 + c1);
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const uint32_t word = b < 2 ? w0 : (b < 4 ? w1 : (b < 6 ? w2 : w3));
-                const int cb = (b & 1) ? (int)(word >> 16) : (int)(word & 0xFFFFu);
-                const int nc = cum + cb;
-                if (b1 < 0 && nc > r1) {
-                    b1 = b;
-                    below1 = cum;
-                    n_in = cb;
-                }
-                if (b2 < 0 && nc > r2) b2 = b;
-                cum = nc;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
-            if (b1 < 0 || b2 < 0) {
-                // cannot happen with a consistent bracket; fall back to the exact bitwise selection over the row
-                state = 3;
+            const int before = below + incl - (int)(c0 + c1);  // values below bin 2L
+            const int cum0 = before + (int)c0, cum1 = cum0 + (int)c1;
+            // first bin whose cumulative count exceeds the rank
+            const unsigned m1 = __ballot_sync(0xffffffffu, cum1 > r1), m2 = __ballot_sync(0xffffffffu, cum1 > r2);
+            if (m1 == 0u || m2 == 0u) {
+                state = 3;  // cannot happen with a consistent bracket: exact bitwise selection over the whole row
                 klo = 0;
                 shift = 32;
                 below = 0;
-            } else if (b1 != b2) {
+                break;
+            }
+            const int l1 = __ffs(m1) - 1, l2 = __ffs(m2) - 1;
+            const int odd1 = __shfl_sync(0xffffffffu, cum0 > r1 ? 0 : 1, l1), odd2 = __shfl_sync(0xffffffffu, cum0 > r2 ? 0 : 1, l2);
+            b1 = 2 * l1 + odd1;
+            b2 = 2 * l2 + odd2;
+            const int below1 = __shfl_sync(0xffffffffu, odd1 ? cum0 : before, l1);
+            const int n1 = __shfl_sync(0xffffffffu, odd1 ? (int)c1 : (int)c0, l1);
+            const int n2 = __shfl_sync(0xffffffffu, odd2 ? (int)c1 : (int)c0, l2);
+            const int n_in = b1 == b2 ? n1 : n1 + n2;
+            if (n_in <= CAND_CAP) {
+                below = below1;
+                state = 1;
+                break;
+            }
+            if (b1 != b2) {
                 state = 2;
                 ksplit = klo + ((uint32_t)b2 << shift);
-            } else {
-                klo += (uint32_t)b1 << shift;
-                below = below1;
-                if (n_in <= CAND_CAP)
-                    state = 1;
-                else if (shift == 0)
-                    state = 3;
-                else
-                    shift = shift >= 3 ? shift - 3 : 0;
+                break;
             }
+            klo += (uint32_t)b1 << shift;
+            below = below1;
+            if (shift == 0) {
+                state = 3;
+                break;
+            }
+            shift = shift >= 6 ? shift - 6 : 0;
+            // refine: histogram of the crowded bin's keys
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hist_mine[q] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            for (int t = 0; t < n_tiles; ++t)
+#pragma unroll
+                for (int i = 0; i < LOUT; ++i) {
+                    const uint32_t d = ((uint32_t)keys_w[t * TILE_V + i * 32] - klo) >> shift;
+                    if (d < (uint32_t)HIST_BINS) hist[d * 32 + lane] += 1;
+                }
         }
 
         double m;
         if (state == 1) {
-            int mine_n = 0;
-            for (int t = 0; t < n_tiles; ++t)
-#pragma unroll
-                for (int i = 0; i < LOUT; ++i) mine_n += ((keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u;
+            // candidates = members of the bin(s) holding the two middle ranks
+            const int mine_n = (int)hist[b1 * 32 + lane] + (b2 != b1 ? (int)hist[b2 * 32 + lane] : 0);
             int incl = mine_n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -367,12 +429,13 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
             }
             const int n = __shfl_sync(0xffffffffu, incl, 31);
             int slot = incl - mine_n;
-            __syncwarp();
             if (mine_n)
                 for (int t = 0; t < n_tiles; ++t)
 #pragma unroll
-                    for (int i = 0; i < LOUT; ++i)
-                        if (((keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u) cand_w[slot++] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
+                    for (int i = 0; i < LOUT; ++i) {
+                        const uint32_t d = ((uint32_t)keys_w[t * TILE_V + i * 32] - klo) >> shift;
+                        if (d == (uint32_t)b1 || d == (uint32_t)b2) cand_w[slot++] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
+                    }
             __syncwarp();
             const double mine = lane < n ? cand_w[lane] : INFINITY;
             int rank = 0;
@@ -386,13 +449,13 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
             const double hi = __shfl_sync(0xffffffffu, mine, (__ffs(q2) - 1) & 31);
             m = (lo + hi) / 2.0;
         } else if (state == 2) {
-            // the two middle ranks sit on either side of a bin boundary: largest value below, smallest above
+            // the two middle ranks sit in different crowded bins: largest value below the split, smallest above
             double lo = -INFINITY, hi = INFINITY;
             for (int t = 0; t < n_tiles; ++t)
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i) {
                     const double x = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
-                    if (keys_w[t * TILE_V + i * 32] < ksplit)
+                    if ((uint32_t)keys_w[t * TILE_V + i * 32] < ksplit)
                         lo = fmax(lo, x);
                     else
                         hi = fmin(hi, x);
@@ -420,7 +483,7 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i)
                             if (i < cnt) {
-                                const bool in_set = shift >= 32 ? true : (((keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u);
+                                const bool in_set = shift >= 32 ? true : ((((uint32_t)keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u);
                                 const unsigned long long ob = ordered_bits64(ldg_keep_f64(src + t * TILE_V + i * 32, pol));
                                 const bool same = bit == 63 ? true : ((ob >> (bit + 1)) == (prefix >> (bit + 1)));
                                 local += in_set && same && !((ob >> bit) & 1ull);
@@ -438,27 +501,37 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
             m = (res[0] + res[1]) / 2.0;
         }
 
-        // ---- centre, row moments, natural-order write
+        // ---- centre, row moments, natural-order write (second read of the row: L2)
         double s = 0.0, ss = 0.0;
-        for (int t = 0; t < n_tiles; ++t) {
-            const int2 g = geom[t * 32 + lane];
-            const int tb = __shfl_sync(0xffffffffu, g.x, 0);
-            const int te = __reduce_max_sync(0xffffffffu, g.x + g.y);
-            double x[LOUT];
+        __syncwarp();  // keys are dead: their space becomes the output staging tile
+        {
+            double xa[LOUT], xb[LOUT];
+            auto emit = [&](const double (&x)[LOUT], int t) {
+                const int2 g = geom[t * 32 + lane];
+                const int tb = __shfl_sync(0xffffffffu, g.x, 0);
+                const int te = __reduce_max_sync(0xffffffffu, g.x + g.y);
 #pragma unroll
-            for (int i = 0; i < LOUT; ++i) x[i] = (i < g.y) ? ldg_keep_f64(src + t * TILE_V + i * 32, pol) : 0.0;
-#pragma unroll
-            for (int i = 0; i < LOUT; ++i)
-                if (i < g.y) {
-                    const double c = x[i] - m;
-                    s += c;
-                    ss = fma(c, c, ss);
-                    stage_w[g.x - tb + i] = (TO)c;
+                for (int i = 0; i < LOUT; ++i)
+                    if (i < g.y) {
+                        const double c = x[i] - m;
+                        s += c;
+                        ss = fma(c, c, ss);
+                        stage_w[g.x - tb + i] = (TO)c;
+                    }
+                __syncwarp();
+                TO* dst = out + row * ldo + tb;
+                for (int k = lane; k < te - tb; k += 32) __stcs(dst + k, stage_w[k]);
+                __syncwarp();
+            };
+            ICNV_LOAD_TILE(xa, 0);
+            for (int t = 0; t < n_tiles; t += 2) {
+                if (t + 1 < n_tiles) ICNV_LOAD_TILE(xb, t + 1);
+                emit(xa, t);
+                if (t + 1 < n_tiles) {
+                    if (t + 2 < n_tiles) ICNV_LOAD_TILE(xa, t + 2);
+                    emit(xb, t + 1);
                 }
-            __syncwarp();
-            TO* dst = out + row * ldo + tb;
-            for (int k = lane; k < te - tb; k += 32) __stcs(dst + k, stage_w[k]);
-            __syncwarp();
+            }
         }
         s = warp_sum_dd(s);
         ss = warp_sum_dd(ss);
@@ -467,6 +540,7 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS) center_rows_kernel(const do
             row_stats[2 * row + 1] = ss;
         }
     }
+#undef ICNV_LOAD_TILE
 }
 
 // Step 5: zero |v| < thr (strict, :451) in place on the natural-order matrix; per-row sum|v| and nnz.
@@ -678,8 +752,7 @@ int aux_center_rows(const double* tmp, int64_t n_rows, int64_t ld, const Task* t
         set_error("icnv_center_rows: more than 28 tiles of tasks per row (byte counters would overflow)");
         return -3;
     }
-    const size_t per_warp = ((size_t)n_tiles * TILE_V * 4 + CAND_CAP * 8 + (size_t)TILE_V * (f64 ? 8 : 4) + 15) / 16 * 16;
-    const size_t smem = ((size_t)n_tiles * 32 * sizeof(int2) + 15) / 16 * 16 + per_warp * CENTER_WARPS;
+    const size_t smem = CenterSmem(n_tiles, CENTER_WARPS).total;
     int dev = 0, n_sm = 148;
     ICNV_CUDA(cudaGetDevice(&dev));
     ICNV_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
