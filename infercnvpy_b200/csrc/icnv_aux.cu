@@ -249,7 +249,8 @@ struct CenterSmem {  // per-warp carve-up, shared by the kernel and its launcher
     size_t key_bytes, per_warp, geom_bytes, total;
     __host__ __device__ CenterSmem(int n_tiles, int warps) {
         // the output tile (<= 8 bytes per value) is staged over the keys, which are dead by then
-        key_bytes = (size_t)n_tiles * TILE_V * 2 > (size_t)TILE_V * 8 ? (size_t)n_tiles * TILE_V * 2 : (size_t)TILE_V * 8;
+        const size_t kb = (size_t)((n_tiles + 1) / 2) * TILE_V * 4;  // two tiles' keys per 32-bit word
+        key_bytes = kb > (size_t)TILE_V * 8 ? kb : (size_t)TILE_V * 8;
         per_warp = (CAND_CAP * 8 + HIST_BINS * 32 + key_bytes + 15) / 16 * 16;
         geom_bytes = ((size_t)n_tiles * 32 * sizeof(int2) + 15) / 16 * 16;
         total = geom_bytes + per_warp * warps;
@@ -269,9 +270,15 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
     int2* geom = reinterpret_cast<int2*>(cr_smem);  // CTA: (column, count) of every task
     unsigned char* wbase = cr_smem + lay.geom_bytes + wib * lay.per_warp;
     double* cand_w = reinterpret_cast<double*>(wbase);
-    unsigned char* hist = wbase + CAND_CAP * 8;  // [64 bins][32 lanes] byte counters
-    TO* stage_w = reinterpret_cast<TO*>(hist + HIST_BINS * 32);
-    uint16_t* keys_w = reinterpret_cast<uint16_t*>(hist + HIST_BINS * 32) + lane;
+    // histogram: word (b >> 2) * 32 + lane holds lane's byte counters of bins 4*(b>>2) .. +3: every access is a
+    // conflict-free 32-bit access to the lane's own bank
+    uint32_t* hist = reinterpret_cast<uint32_t*>(wbase + CAND_CAP * 8);
+    TO* stage_w = reinterpret_cast<TO*>(hist + HIST_BINS * 8);
+    // keys: word (pair * LOUT + i) * 32 + lane = key of (tile 2*pair, slot i) | key of (tile 2*pair+1, slot i) << 16
+    uint32_t* keys_w = reinterpret_cast<uint32_t*>(hist + HIST_BINS * 8) + lane;
+    uint32_t* hist_l = hist + lane;
+    auto hist_inc = [&](uint32_t b) { hist_l[(b >> 2) * 32] += 1u << ((b & 3u) << 3); };
+    auto hist_get = [&](int b) { return (int)((hist_l[(b >> 2) * 32] >> ((b & 3) << 3)) & 0xFFu); };
     for (int ti = threadIdx.x; ti < n_tiles * 32; ti += blockDim.x) {
         int2 g = make_int2(0, 0);
         if (ti < n_tasks) {
@@ -287,7 +294,10 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
     const int64_t n_warps = (int64_t)gridDim.x * CENTER_WARPS;
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
     const float invK = 1.f / (float)K;
-    uint4* hist_mine = reinterpret_cast<uint4*>(hist) + lane * 4;  // lane L sums / clears bins 2L and 2L+1 (64 bytes)
+    uint4* hist_clear = reinterpret_cast<uint4*>(hist) + lane * 4;  // 64 bytes per lane
+    // lane L totals bins 2L and 2L+1: bytes (2L & 3) and +1 of row L >> 1, all 32 lanes' words (skewed 16-byte reads)
+    const uint4* hist_row = reinterpret_cast<const uint4*>(hist + (lane >> 1) * 32);
+    const uint32_t sel0 = (lane & 1) ? 0x00010000u : 0x00000001u, sel1 = sel0 << 8;
 
 #define ICNV_LOAD_TILE(X, T) \
     _Pragma("unroll") for (int i = 0; i < LOUT; ++i) X[i] = ldg_keep_f64(src + (T) * TILE_V + i * 32, pol)
@@ -313,27 +323,35 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
         const double kscale = (double)(32768.f / half);
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) hist_mine[q] = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 4; ++q) hist_clear[q] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
         // ---- keys + level-0 histogram; two tiles of loads in flight per lane
         {
             double xa[LOUT], xb[LOUT];
-            auto key_tile = [&](const double (&x)[LOUT], int t) {
+            ICNV_LOAD_TILE(xa, 0);
+            if (1 < n_tiles) ICNV_LOAD_TILE(xb, 1);
+            for (int t = 0; t < n_tiles; t += 2) {
+                uint32_t kk[LOUT];
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i) {
-                    const uint16_t k = key16_sat((x[i] - kbase) * kscale);
-                    keys_w[t * TILE_V + i * 32] = k;
-                    hist[((uint32_t)k >> 10) * 32 + lane] += 1;
+                    kk[i] = key16_sat((xa[i] - kbase) * kscale);
+                    hist_inc(kk[i] >> 10);
                 }
-            };
-            ICNV_LOAD_TILE(xa, 0);
-            for (int t = 0; t < n_tiles; t += 2) {
-                if (t + 1 < n_tiles) ICNV_LOAD_TILE(xb, t + 1);
-                key_tile(xa, t);
+                if (t + 2 < n_tiles) ICNV_LOAD_TILE(xa, t + 2);
                 if (t + 1 < n_tiles) {
-                    if (t + 2 < n_tiles) ICNV_LOAD_TILE(xa, t + 2);
-                    key_tile(xb, t + 1);
+#pragma unroll
+                    for (int i = 0; i < LOUT; ++i) {
+                        const uint32_t kb = key16_sat((xb[i] - kbase) * kscale);
+                        hist_inc(kb >> 10);
+                        kk[i] |= kb << 16;
+                    }
+                    if (t + 3 < n_tiles) ICNV_LOAD_TILE(xb, t + 3);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < LOUT; ++i) kk[i] |= 0xFFFF0000u;
                 }
+#pragma unroll
+                for (int i = 0; i < LOUT; ++i) keys_w[((t >> 1) * LOUT + i) * 32] = kk[i];
             }
         }
 
@@ -343,24 +361,17 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
             __syncwarp();
             // bin totals: lane L owns bins 2L, 2L+1
             uint32_t c0 = 0, c1 = 0;
-            {
-                const uint4 h0 = hist_mine[0], h1 = hist_mine[1], h2 = hist_mine[2], h3 = hist_mine[3];
-                c0 = __dp4a(h0.x, 0x01010101u, c0);
-                c0 = __dp4a(h0.y, 0x01010101u, c0);
-                c0 = __dp4a(h0.z, 0x01010101u, c0);
-                c0 = __dp4a(h0.w, 0x01010101u, c0);
-                c0 = __dp4a(h1.x, 0x01010101u, c0);
-                c0 = __dp4a(h1.y, 0x01010101u, c0);
-                c0 = __dp4a(h1.z, 0x01010101u, c0);
-                c0 = __dp4a(h1.w, 0x01010101u, c0);
-                c1 = __dp4a(h2.x, 0x01010101u, c1);
-                c1 = __dp4a(h2.y, 0x01010101u, c1);
-                c1 = __dp4a(h2.z, 0x01010101u, c1);
-                c1 = __dp4a(h2.w, 0x01010101u, c1);
-                c1 = __dp4a(h3.x, 0x01010101u, c1);
-                c1 = __dp4a(h3.y, 0x01010101u, c1);
-                c1 = __dp4a(h3.z, 0x01010101u, c1);
-                c1 = __dp4a(h3.w, 0x01010101u, c1);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 v = hist_row[(q + (lane >> 1)) & 7];
+                c0 = __dp4a(v.x, sel0, c0);
+                c0 = __dp4a(v.y, sel0, c0);
+                c0 = __dp4a(v.z, sel0, c0);
+                c0 = __dp4a(v.w, sel0, c0);
+                c1 = __dp4a(v.x, sel1, c1);
+                c1 = __dp4a(v.y, sel1, c1);
+                c1 = __dp4a(v.z, sel1, c1);
+                c1 = __dp4a(v.w, sel1, c1);
             }
             int incl = (int)(c0 + c1);
 #pragma unroll
@@ -407,20 +418,22 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
             // refine: histogram of the crowded bin's keys
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hist_mine[q] = make_uint4(0u, 0u, 0u, 0u);
+            for (int q = 0; q < 4; ++q) hist_clear[q] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
-            for (int t = 0; t < n_tiles; ++t)
+            for (int t = 0; t < n_tiles; t += 2)
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i) {
-                    const uint32_t d = ((uint32_t)keys_w[t * TILE_V + i * 32] - klo) >> shift;
-                    if (d < (uint32_t)HIST_BINS) hist[d * 32 + lane] += 1;
+                    const uint32_t w = keys_w[((t >> 1) * LOUT + i) * 32];
+                    const uint32_t da = ((w & 0xFFFFu) - klo) >> shift, db = ((w >> 16) - klo) >> shift;
+                    if (da < (uint32_t)HIST_BINS) hist_inc(da);
+                    if (db < (uint32_t)HIST_BINS && t + 1 < n_tiles) hist_inc(db);
                 }
         }
 
         double m;
         if (state == 1) {
             // candidates = members of the bin(s) holding the two middle ranks
-            const int mine_n = (int)hist[b1 * 32 + lane] + (b2 != b1 ? (int)hist[b2 * 32 + lane] : 0);
+            const int mine_n = hist_get(b1) + (b2 != b1 ? hist_get(b2) : 0);
             int incl = mine_n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -430,11 +443,14 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
             const int n = __shfl_sync(0xffffffffu, incl, 31);
             int slot = incl - mine_n;
             if (mine_n)
-                for (int t = 0; t < n_tiles; ++t)
+                for (int t = 0; t < n_tiles; t += 2)
 #pragma unroll
                     for (int i = 0; i < LOUT; ++i) {
-                        const uint32_t d = ((uint32_t)keys_w[t * TILE_V + i * 32] - klo) >> shift;
-                        if (d == (uint32_t)b1 || d == (uint32_t)b2) cand_w[slot++] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
+                        const uint32_t w = keys_w[((t >> 1) * LOUT + i) * 32];
+                        const uint32_t da = ((w & 0xFFFFu) - klo) >> shift, db = ((w >> 16) - klo) >> shift;
+                        if (da == (uint32_t)b1 || da == (uint32_t)b2) cand_w[slot++] = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
+                        if ((db == (uint32_t)b1 || db == (uint32_t)b2) && t + 1 < n_tiles)
+                            cand_w[slot++] = ldg_keep_f64(src + (t + 1) * TILE_V + i * 32, pol);
                     }
             __syncwarp();
             const double mine = lane < n ? cand_w[lane] : INFINITY;
@@ -455,7 +471,8 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
 #pragma unroll
                 for (int i = 0; i < LOUT; ++i) {
                     const double x = ldg_keep_f64(src + t * TILE_V + i * 32, pol);
-                    if ((uint32_t)keys_w[t * TILE_V + i * 32] < ksplit)
+                    const uint32_t w = keys_w[((t >> 1) * LOUT + i) * 32];
+                    if (((t & 1) ? (w >> 16) : (w & 0xFFFFu)) < ksplit)
                         lo = fmax(lo, x);
                     else
                         hi = fmin(hi, x);
@@ -483,7 +500,9 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i)
                             if (i < cnt) {
-                                const bool in_set = shift >= 32 ? true : ((((uint32_t)keys_w[t * TILE_V + i * 32] - klo) >> shift) == 0u);
+                                const uint32_t w = keys_w[((t >> 1) * LOUT + i) * 32];
+                                const uint32_t kx = (t & 1) ? (w >> 16) : (w & 0xFFFFu);
+                                const bool in_set = shift >= 32 ? true : (((kx - klo) >> shift) == 0u);
                                 const unsigned long long ob = ordered_bits64(ldg_keep_f64(src + t * TILE_V + i * 32, pol));
                                 const bool same = bit == 63 ? true : ((ob >> (bit + 1)) == (prefix >> (bit + 1)));
                                 local += in_set && same && !((ob >> bit) & 1ull);
