@@ -19,6 +19,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // aux launchers (icnv_aux.cu)
 int aux_colsum_dense(const float*, int64_t, int64_t, int, const int32_t*, int, double*, int64_t*, double*, int, cudaStream_t);
+int aux_colsum_dense_slots(int* slots);
 int aux_colsum_csr(const int64_t*, const int32_t*, const float*, int64_t, int, const int32_t*, int, double*, int64_t*, cudaStream_t);
 int aux_mean_from_sums(const double*, const int64_t*, int, int, void*, bool, cudaStream_t);
 int aux_nnz_to_indptr(const int32_t*, int64_t, int64_t*, cudaStream_t);
@@ -458,8 +459,12 @@ int icnv_colsum_dense_f32(const float* X, int64_t n_rows, int64_t ldx, int32_t G
         set_error("icnv_colsum_dense_f32: bad argument");
         return ICNV_EINVAL;
     }
-    // row splits: enough CTAs to fill the machine, each with a decent run of rows
-    int n_split = (int)std::min<int64_t>(std::max<int64_t>(1, n_rows / 64), 4 * 148 / std::max(1, (G + 1023) / 1024) + 1);
+    // row splits: exactly one wave of resident CTAs (a partial second wave idles most of the machine), each with a
+    // decent run of rows
+    int slots = 0;
+    if (aux_colsum_dense_slots(&slots)) return ICNV_ECUDA;
+    const int64_t per_split = (int64_t)std::max(1, (G + 1023) / 1024) * n_cat;
+    int n_split = (int)std::min<int64_t>(std::max<int64_t>(1, n_rows / 64), std::max<int64_t>(1, slots / per_split));
     // grow-only per-device workspace for the [split][cat][G] partial sums (stream-ordered use only)
     static double* ws[16] = {nullptr};
     static size_t ws_bytes[16] = {0};

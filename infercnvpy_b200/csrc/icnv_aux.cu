@@ -12,7 +12,7 @@ namespace icnv {
 // in flight.  fp64 accumulation; partials [split][cat][G] are reduced in a fixed order afterwards so
 // the result is run-to-run deterministic.
 template <bool VEC>
-__global__ void __launch_bounds__(256) colsum_dense_kernel(const float* __restrict__ X, int64_t n_rows, int64_t ldx,
+__global__ void __launch_bounds__(256, 4) colsum_dense_kernel(const float* __restrict__ X, int64_t n_rows, int64_t ldx,
                                                            int G, const int32_t* __restrict__ row_cat,
                                                            double* __restrict__ partial) {
     const int cat = blockIdx.z;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
     const int64_t n_warps = (int64_t)gridDim.x * CENTER_WARPS;
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
     const float invK = 1.f / (float)K;
-    uint4* hist_clear = reinterpret_cast<uint4*>(hist) + lane * 4;  // 64 bytes per lane
+    uint4* hist_clear = reinterpret_cast<uint4*>(hist) + lane;  // 4 x 16 bytes per lane, lanes contiguous
     // lane L totals bins 2L and 2L+1: bytes (2L & 3) and +1 of row L >> 1, all 32 lanes' words (skewed 16-byte reads)
     const uint4* hist_row = reinterpret_cast<const uint4*>(hist + (lane >> 1) * 32);
     const uint32_t sel0 = (lane & 1) ? 0x00010000u : 0x00000001u, sel1 = sel0 << 8;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
         const double kscale = (double)(32768.f / half);
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) hist_clear[q] = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 4; ++q) hist_clear[q * 32] = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
         // ---- keys + level-0 histogram; two tiles of loads in flight per lane
         {
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
             // refine: histogram of the crowded bin's keys
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) hist_clear[q] = make_uint4(0u, 0u, 0u, 0u);
+            for (int q = 0; q < 4; ++q) hist_clear[q * 32] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             for (int t = 0; t < n_tiles; t += 2)
 #pragma unroll
@@ -690,6 +690,26 @@ static int grid_for_rows(int64_t n_rows) {
     if (g < 1) g = 1;
     if (g > 148 * 8) g = 148 * 8;
     return (int)g;
+}
+
+// resident CTAs of the dense column-sum kernel on the current device (cached per device)
+int aux_colsum_dense_slots(int* slots) {
+    static int cached[16] = {0};
+    int dev = 0;
+    ICNV_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16 || cached[dev] == 0) {
+        int n_sm = 0, occ = 0;
+        ICNV_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, colsum_dense_kernel<true>, 256, 0));
+        const int v = n_sm * (occ > 0 ? occ : 1);
+        if (dev < 0 || dev >= 16) {
+            *slots = v;
+            return 0;
+        }
+        cached[dev] = v;
+    }
+    *slots = cached[dev];
+    return 0;
 }
 
 int aux_colsum_dense(const float* X, int64_t n_rows, int64_t ldx, int G, const int32_t* row_cat, int n_cat, double* sums,
