@@ -261,7 +261,8 @@ template <typename TO>
 __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const double* __restrict__ tmp, int64_t n_rows, int64_t ld,
                                                                            const Task* __restrict__ tasks, int n_tasks, int K,
                                                                            TO* __restrict__ out, int64_t ldo,
-                                                                           double* __restrict__ row_stats) {
+                                                                           double* __restrict__ row_stats,
+                                                                           unsigned long long* __restrict__ next_row) {
     extern __shared__ __align__(16) unsigned char cr_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n_tiles = (n_tasks + 31) >> 5;
@@ -290,8 +291,13 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
     __syncthreads();
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    const int64_t warp = (int64_t)blockIdx.x * CENTER_WARPS + wib;
-    const int64_t n_warps = (int64_t)gridDim.x * CENTER_WARPS;
+    // rows are handed out dynamically (refinement levels make their cost uneven, and a static split leaves a tail);
+    // a warp fetches its next row index while it works on the current one
+    auto grab = [&]() {
+        unsigned long long r = 0;
+        if (lane == 0) r = atomicAdd(next_row, 1ull);
+        return (int64_t)__shfl_sync(0xffffffffu, r, 0);
+    };
     const int r1 = (K - 1) >> 1, r2 = K >> 1;
     const float invK = 1.f / (float)K;
     uint4* hist_clear = reinterpret_cast<uint4*>(hist) + lane;  // 4 x 16 bytes per lane, lanes contiguous
@@ -302,7 +308,10 @@ __global__ void __launch_bounds__(32 * CENTER_WARPS, 3) center_rows_kernel(const
 #define ICNV_LOAD_TILE(X, T) \
     _Pragma("unroll") for (int i = 0; i < LOUT; ++i) X[i] = ldg_keep_f64(src + (T) * TILE_V + i * 32, pol)
 
-    for (int64_t row = warp; row < n_rows; row += n_warps) {
+    int64_t row_next = grab();
+    while (row_next < n_rows) {
+        const int64_t row = row_next;
+        row_next = grab();
         const double* src = tmp + row * ld + lane;
         // ---- location / scale (fp32, steers the bracket only)
         float f1 = 0.f, f2 = 0.f;
@@ -800,12 +809,22 @@ int aux_center_rows(const double* tmp, int64_t n_rows, int64_t ld, const Task* t
     if (per_sm < 1) per_sm = 1;
     const int64_t want = (n_rows + CENTER_WARPS - 1) / CENTER_WARPS;
     const int grid = (int)(want < (int64_t)n_sm * per_sm ? want : (int64_t)n_sm * per_sm);
+    // per-device row counter (stream-ordered use, like the column-sum workspace)
+    static unsigned long long* counter[16] = {nullptr};
+    if (dev < 0 || dev >= 16) {
+        set_error("icnv_center_rows: device index out of range");
+        return -1;
+    }
+    if (!counter[dev]) ICNV_CUDA(cudaMalloc(&counter[dev], sizeof(unsigned long long)));
+    ICNV_CUDA(cudaMemsetAsync(counter[dev], 0, sizeof(unsigned long long), st));
     if (f64) {
         ICNV_CUDA(cudaFuncSetAttribute(center_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        center_rows_kernel<double><<<grid, 32 * CENTER_WARPS, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (double*)out, ldo, row_stats);
+        center_rows_kernel<double><<<grid, 32 * CENTER_WARPS, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (double*)out, ldo, row_stats,
+                                                                        counter[dev]);
     } else {
         ICNV_CUDA(cudaFuncSetAttribute(center_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        center_rows_kernel<float><<<grid, 32 * CENTER_WARPS, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (float*)out, ldo, row_stats);
+        center_rows_kernel<float><<<grid, 32 * CENTER_WARPS, smem, st>>>(tmp, n_rows, ld, tasks, n_tasks, K, (float*)out, ldo, row_stats,
+                                                                       counter[dev]);
     }
     ICNV_CUDA(cudaGetLastError());
     return 0;

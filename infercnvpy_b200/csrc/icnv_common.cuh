@@ -10,7 +10,10 @@ namespace icnv {
 
 constexpr int NT = 512;         // threads per CTA of the smoothing kernel
 constexpr int NW = NT / 32;     // warps per CTA
-constexpr int LOUT = 9;         // consecutive outputs owned by one task (9*16 B stride -> conflict-free LDS.128)
+#ifndef ICNV_LOUT
+#define ICNV_LOUT 9
+#endif
+constexpr int LOUT = ICNV_LOUT;         // consecutive outputs owned by one task (9*16 B stride -> conflict-free LDS.128)
 constexpr int CAND_CAP = 32;    // median: size of the final exact candidate set
 constexpr int PAD_GROUPS = 12;  // slack groups after the last one (sliding window over-read, >= LOUT)
 

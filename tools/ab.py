@@ -23,5 +23,5 @@ else:
             for ln in r.stdout.splitlines():
                 if '"window"' in ln:
                     import json; d = json.loads(ln)
-                    print(f"{name:12s} w{d['window']} smooth_ms={d['smooth_ms'][0]:.4f} frac={d['smooth_frac']:.4f}")
+                    print(f"{name:12s} w{d['window']} smooth_ms={d['smooth_ms'][0]:.4f} frac={d['smooth_frac']:.4f} center_ms={d['center_ms'][0]:.4f} colsum_ms={d['colsum_ms'][0]:.4f} thr_ms={d['thr_ms'][0]:.4f}")
             if r.returncode: print(name, "FAILED", r.stderr[-500:])
