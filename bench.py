@@ -334,8 +334,14 @@ def main():
         if container == "csr":
             import scipy.sparse as sp
 
-            ip, ix, dv = (x.cpu().numpy() for x in Xin)
-            Xhost = sp.csr_matrix((dv, ix, ip), shape=(n_local, G_GENES))
+            def pinned_np(t):  # like the dense arm: the host container lives in pinned memory
+                h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                h.copy_(t)
+                return h.numpy()
+
+            ip, ix, dv = (pinned_np(x) for x in Xin)
+            Xhost = sp.csr_matrix((dv, ix, ip), shape=(n_local, G_GENES), copy=False)
+            Xhost.has_canonical_format = True  # produced by torch's to_sparse_csr: sorted, no duplicates
         else:
             host = torch.empty((n_e2e, G_GENES), dtype=torch.float32, pin_memory=True)
             host.copy_(Xd)

@@ -33,17 +33,74 @@ def _rows_to_device(expr, r0, r1, device):
     import torch
 
     if scipy.sparse.issparse(expr):
-        blk = expr[r0:r1].tocsr()
-        blk.sort_indices()
-        return (
-            torch.from_numpy(blk.indptr.astype(np.int64)).to(device),
-            torch.from_numpy(blk.indices.astype(np.int32)).to(device),
-            torch.from_numpy(blk.data.astype(np.float32)).to(device),
+        whole = r0 == 0 and r1 == expr.shape[0] and expr.format == "csr"
+        blk = expr if whole else expr[r0:r1].tocsr()
+        triple = (
+            _upload_1d(blk.indptr.astype(np.int64, copy=False), device),
+            _upload_1d(blk.indices.astype(np.int32, copy=False), device),
+            _upload_1d(blk.data.astype(np.float32, copy=False), device),
         )
+        if not _csr_is_canonical(*triple):
+            # duplicates / unsorted columns: scipy's toarray() sums duplicates (_infercnv.py:423); canonicalise on
+            # the host (rare) and upload again
+            blk = blk.copy()
+            blk.sum_duplicates()
+            triple = (
+                _upload_1d(blk.indptr.astype(np.int64, copy=False), device),
+                _upload_1d(blk.indices.astype(np.int32, copy=False), device),
+                _upload_1d(blk.data.astype(np.float32, copy=False), device),
+            )
+        return triple
     if isinstance(expr, torch.Tensor):
         return expr[r0:r1].to(device=device, dtype=torch.float32).contiguous()
     blk = np.ascontiguousarray(np.asarray(expr[r0:r1]), dtype=np.float32)
     return torch.from_numpy(blk).to(device)
+
+
+def _upload_1d(arr: np.ndarray, device):
+    """Host 1-D array -> device tensor.  Pinned sources go as one async DMA; large pageable ones are staged through
+    two pinned buffers so the host memcpy of slab i+1 overlaps the DMA of slab i."""
+    import torch
+
+    arr = np.ascontiguousarray(arr)
+    src = torch.from_numpy(arr)
+    n = src.numel()
+    if n * src.element_size() < (64 << 20):
+        return src.to(device)
+    dst = torch.empty((n,), dtype=src.dtype, device=device)
+    if src.is_pinned():
+        dst.copy_(src, non_blocking=True)
+        return dst
+    slab = (128 << 20) // src.element_size()
+    staging = [torch.empty((slab,), dtype=src.dtype, pin_memory=True) for _ in range(2)]
+    done = [None, None]
+    for i, a in enumerate(range(0, n, slab)):
+        b = min(n, a + slab)
+        buf = staging[i % 2]
+        if done[i % 2] is not None:
+            done[i % 2].synchronize()
+        buf[: b - a].copy_(src[a:b])
+        dst[a:b].copy_(buf[: b - a], non_blocking=True)
+        done[i % 2] = torch.cuda.Event()
+        done[i % 2].record()
+    for ev in done:
+        if ev is not None:
+            ev.synchronize()
+    return dst
+
+
+def _csr_is_canonical(indptr, indices, data) -> bool:
+    """Column indices strictly increasing inside every row (checked on the device: one pass over ``indices``)."""
+    import torch
+
+    nnz = indices.numel()
+    if nnz < 2:
+        return True
+    bad = indices[1:] <= indices[:-1]
+    starts = indptr[1:-1]
+    starts = starts[(starts > 0) & (starts < nnz)]
+    bad[starts - 1] = False  # a new row may start with any column
+    return not bool(bad.any().item())
 
 
 def _upload_pipelined(expr: np.ndarray, device, on_slab):

@@ -176,6 +176,35 @@ def test_layer_equals_x():
     assert (a.obsm["X_cnv"] != b.obsm["X_cnv"]).nnz == 0
 
 
+def test_csr_with_duplicates_and_unsorted_columns_equals_dense():
+    # scipy's toarray() (_infercnv.py:423) sums duplicate entries and does not care about column order
+    import scipy.sparse as sp
+
+    var = cnv.datasets.synthetic_var(2400, seed=0)
+    X = cnv.datasets.synthetic_counts(70, 2400, seed=9)
+    csr = sp.csr_matrix(X)
+    # split every stored value into two halves stored at the same (row, col), then shuffle the columns of each row
+    rng = np.random.default_rng(0)
+    indptr, indices, data = [0], [], []
+    for r in range(X.shape[0]):
+        cols = csr.indices[csr.indptr[r] : csr.indptr[r + 1]]
+        vals = csr.data[csr.indptr[r] : csr.indptr[r + 1]]
+        c2 = np.concatenate([cols, cols])
+        v2 = np.concatenate([vals * np.float32(0.5), vals * np.float32(0.5)])
+        perm = rng.permutation(len(c2))
+        indices.append(c2[perm])
+        data.append(v2[perm])
+        indptr.append(indptr[-1] + len(c2))
+    messy = sp.csr_matrix((np.concatenate(data), np.concatenate(indices), np.array(indptr)), shape=X.shape)
+    assert not messy.has_canonical_format
+    np.testing.assert_array_equal(messy.toarray(), X)
+    a = cnv.AnnData(messy, var=var)
+    b = cnv.AnnData(csr, var=var)
+    cnv.tl.infercnv(a)
+    cnv.tl.infercnv(b)
+    assert (a.obsm["X_cnv"] != b.obsm["X_cnv"]).nnz == 0
+
+
 # ---- size-independent properties at (close to) bench shape ----------------------------------------
 def test_properties_at_scale():
     torch = _torch()
