@@ -2,7 +2,7 @@
 // (centre, clip, per-chromosome pyramid running mean decimated by `step`) for one cell row per CTA
 // iteration, persistent CTAs.  Step 4 (row median) and step 5 (noise filter) are icnv_aux.cu's
 // center_rows_kernel / threshold kernel: an exact median is a long serial chain per row, and inside this
-// kernel it held every row's CTA for ~7k cycles (ablation in profiles/ab_ablation_r1.txt: 42 % -> 58 % of the HBM
+// kernel it held every row's CTA for ~7k cycles (ablation in profiles/ablation_r1.txt: 42 % -> 58 % of the HBM
 // roofline without it); one warp per row with thousands of independent warps hides that latency.
 //
 // Data flow per row (tiers 0/1, "grouped"):
