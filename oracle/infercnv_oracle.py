@@ -153,20 +153,57 @@ def running_mean(x: np.ndarray, n: int, step: int) -> np.ndarray:
     return out / np.sum(flat)
 
 
-def smooth_by_chromosome(x: np.ndarray, chromosome, start, window: int, step: int):
+def gene_values_for_segment(smoothed: np.ndarray, width: int, n: int, step: int):
+    """Per-gene values of one chromosome.  tl/_infercnv.py:214-223, 238-242, 247-291.
+
+    Regular branch: the value of the gene at sorted position ``p`` is ``np.mean`` of the decimated
+    windows ``k`` that contain it (``k*step <= p < k*step + n``), in window order
+    (``_calculate_gene_averages`` appends them left to right and takes ``np.mean`` of the list,
+    ``:278-287``); genes no kept window covers do not appear at all.  Flat branch
+    (``width <= n``): every gene gets the single flat mean (``:240``).
+    Returns ``(positions, values [rows, len(positions)])``.
+    """
+    rows = smoothed.shape[0]
+    if n < width:
+        n_out = smoothed.shape[1]
+        pos, cols = [], []
+        for p in range(width):
+            k_lo = max(0, -((n - 1 - p) // step))  # ceil((p - n + 1) / step)
+            k_hi = min(n_out - 1, p // step)
+            if k_lo > k_hi:
+                continue
+            pos.append(p)
+            # np.mean of a 1-D float64 array: add.reduce (pairwise) then divide by the count
+            block = np.ascontiguousarray(smoothed[:, k_lo : k_hi + 1], dtype=np.float64)
+            cols.append(np.array([np.mean(block[r]) for r in range(rows)]))
+        vals = np.stack(cols, axis=1) if cols else np.empty((rows, 0))
+        return np.asarray(pos, dtype=np.int64), vals
+    return np.arange(width, dtype=np.int64), np.repeat(smoothed, width, axis=1)
+
+
+def smooth_by_chromosome(x: np.ndarray, chromosome, start, window: int, step: int, gene_values: bool = False):
     """tl/_infercnv.py:301-343 — smooth every chromosome on its own and stack.
 
     Returns ``(chr_pos, smoothed)`` where ``chr_pos[chr]`` is the first output
     column of that chromosome (``:335-337``, numpy ints from ``np.cumsum``).
     """
     order = natural_chromosome_order(chromosome)
-    pieces = [running_mean(x[:, gene_order(chromosome, start, c)], window, step) for c in order]
+    genes = [gene_order(chromosome, start, c) for c in order]
+    pieces = [running_mean(x[:, g], window, step) for g in genes]
     offsets = np.cumsum([0] + [p.shape[1] for p in pieces])
     chr_pos = {c: off for c, off in zip(order, offsets)}
-    return chr_pos, np.hstack(pieces)
+    if not gene_values:
+        return chr_pos, np.hstack(pieces)
+    # per-gene values, concatenated over chromosomes (:339-341); ``gene_cols`` are the matrix columns they belong to
+    gene_cols, gene_vals = [], []
+    for g, piece in zip(genes, pieces):
+        pos, vals = gene_values_for_segment(piece, len(g), window, step)
+        gene_cols.append(np.asarray(g)[pos])
+        gene_vals.append(vals)
+    return chr_pos, np.hstack(pieces), np.concatenate(gene_cols), np.hstack(gene_vals)
 
 
-def infercnv_chunk(x, chromosome, start, reference, lfc_clip, window, step, dynamic_threshold):
+def infercnv_chunk(x, chromosome, start, reference, lfc_clip, window, step, dynamic_threshold, gene_values=False):
     """One row-chunk of the method.  tl/_infercnv.py:411-457.
 
     1. centre: one reference row -> ``x - ref`` (``:422-423``); several ->
@@ -193,11 +230,22 @@ def infercnv_chunk(x, chromosome, start, reference, lfc_clip, window, step, dyna
         centred[below] = _as_ndarray(x - lo)[below]
     centred = np.asarray(_as_ndarray(centred))
     clipped = np.clip(centred, -lfc_clip, lfc_clip)
-    chr_pos, smoothed = smooth_by_chromosome(clipped, chromosome, start, window, step)
+    if gene_values:
+        chr_pos, smoothed, gene_cols, conv = smooth_by_chromosome(clipped, chromosome, start, window, step, True)
+    else:
+        chr_pos, smoothed = smooth_by_chromosome(clipped, chromosome, start, window, step)
     res = smoothed - np.median(smoothed, axis=1)[:, np.newaxis]
+    gene_res = None
+    if gene_values:
+        # the per-gene layer is centred on ITS OWN row median (:444) but filtered with the window threshold (:453)
+        gene_res = conv - np.median(conv, axis=1)[:, np.newaxis]
     if dynamic_threshold is not None:
         thr = dynamic_threshold * np.std(res)
         res[np.abs(res) < thr] = 0
+        if gene_values:
+            gene_res[np.abs(gene_res) < thr] = 0
+    if gene_values:
+        return chr_pos, sp.csr_matrix(res), (gene_cols, gene_res)
     return chr_pos, sp.csr_matrix(res)
 
 
@@ -220,6 +268,7 @@ def infercnv(
     exclude_chromosomes=("chrX", "chrY"),
     chunksize=5000,
     n_jobs=1,
+    calculate_gene_values=False,
 ):
     """Whole-matrix driver.  tl/_infercnv.py:97-161.
 
@@ -230,7 +279,8 @@ def infercnv(
     (``:137``); ``chr_pos`` is taken from the first chunk (``:139``).
     ``n_jobs`` > 1 fans the chunks out to a process pool like the reference's
     ``process_map`` (``:121,132``).
-    Returns ``(chr_pos, csr float64 [N, K])``.
+    Returns ``(chr_pos, csr float64 [N, K])``; with ``calculate_gene_values`` also the per-gene matrix
+    ``[N, n_var]`` float64, NaN for genes no kept window covers and for masked genes (``:141-148``).
     """
     chrom_s = pd.Series(np.asarray(chromosome, dtype=object))
     drop = chrom_s.isnull()
@@ -246,7 +296,8 @@ def infercnv(
     start_k = np.asarray(start)[keep]
 
     jobs = [
-        (expr[i : i + chunksize, :], chrom_k, start_k, ref, lfc_clip, window_size, step, dynamic_threshold)
+        (expr[i : i + chunksize, :], chrom_k, start_k, ref, lfc_clip, window_size, step, dynamic_threshold,
+         calculate_gene_values)
         for i in range(0, X.shape[0], chunksize)
     ]
     if n_jobs is None or n_jobs > 1:
@@ -255,7 +306,16 @@ def infercnv(
     else:
         results = [_chunk_job(j) for j in jobs]
     chr_pos = results[0][0]
-    return chr_pos, sp.vstack([r[1] for r in results])
+    res = sp.vstack([r[1] for r in results])
+    if not calculate_gene_values:
+        return chr_pos, res
+    kept_to_var = np.flatnonzero(keep)
+    per_gene = np.full((X.shape[0], X.shape[1]), np.nan)
+    r0 = 0
+    for _, blk, (cols, vals) in results:
+        per_gene[r0 : r0 + blk.shape[0], kept_to_var[cols]] = vals
+        r0 += blk.shape[0]
+    return chr_pos, res, per_gene
 
 
 # --------------------------------------------------------------------------- #

@@ -63,3 +63,19 @@ X_RES_ACTUAL = np.array(
 @pytest.fixture()
 def x_res_actual():
     return X_RES_ACTUAL.copy()
+
+
+# /root/reference/tests/conftest.py:78-95 (columns gene1..gene10, rows = the 4 cells)
+GENE_RES_ACTUAL = np.array(
+    [
+        [0.75, 0.00, 0.000000, 0.00, -0.75, 0.000000, 0.000000, 0.0, 0.0, 0.75],
+        [-1.00, 0.00, 0.000000, 0.00, 0.00, 0.000000, 0.000000, 0.0, 0.0, 0.00],
+        [0.00, 0.75, 0.91666667, 1.25, 1.25, 0.000000, 0.000000, 0.0, 0.0, 0.00],
+        [0.00, 0.00, 0.000000, 0.00, 0.00, 0.921875, 0.703125, 0.0, 0.0, 0.00],
+    ]
+)
+
+
+@pytest.fixture()
+def gene_res_actual():
+    return GENE_RES_ACTUAL.copy()

@@ -55,6 +55,20 @@ CASES = [
     # bench-shaped gene axis: G = 20000 with the SURVEY var spec -> K = 1792 / 1463
     dict(name="g20k_win100", n=48, g=20000, extras=False, kw=dict(chunksize=32)),
     dict(name="g20k_win250", n=24, g=20000, extras=False, kw=dict(window_size=250, chunksize=5000)),
+    # ---- calculate_gene_values=True (:141-151, :220-223, :247-291, :443-444, :452-453): per-gene layer ----
+    # masked genes + flat chromosomes + three chunks
+    dict(name="gv_small", n=24, g=2400, extras=True, seed=2001, gene_values=True, kw=dict(chunksize=10)),
+    # step does not divide the window; uncovered tail genes -> NaN
+    dict(name="gv_win11_step3", n=16, g=1500, extras=False, seed=2002, gene_values=True,
+         kw=dict(window_size=11, step=3, chunksize=5000)),
+    # step > window: genes between kept windows are not covered at all
+    dict(name="gv_win10_step20", n=12, g=1500, extras=True, seed=2003, gene_values=True,
+         kw=dict(window_size=10, step=20, chunksize=5)),
+    # bounded centring, no noise filter
+    dict(name="gv_cats_nothr", n=20, g=2400, extras=True, seed=2004, obs_cats=3, gene_values=True,
+         kw=dict(chunksize=8, dynamic_threshold=None, reference_key="cell_type", reference_cat=["c0", "c1"])),
+    # bench-shaped gene axis
+    dict(name="gv_g20k", n=8, g=20000, extras=False, seed=2005, gene_values=True, kw=dict(chunksize=5)),
 ]
 
 

@@ -10,7 +10,8 @@ drifting RNG stream is caught instead of silently comparing different data.
 What is stored per case: the reference profile that the reference computed
 (``_get_reference``), ``chr_pos`` and the CSR float64 result of the public
 ``infercnv()`` (``/root/reference/src/infercnvpy/tl/_infercnv.py:18-161``), and
-for some cases ``cnv_score`` (``tl/_scores.py:14-74``).
+for some cases ``cnv_score`` (``tl/_scores.py:14-74``) or the per-gene layer of
+``calculate_gene_values=True``.  ``python tests/golden/make_golden.py NAME ...`` regenerates only those cases.
 """
 
 from __future__ import annotations
@@ -43,7 +44,9 @@ def run_reference(case):
         adata, kw.get("reference_key"), kw.get("reference_cat"), kw.get("reference"), None
     )
     profile = np.asarray(profile)
-    chr_pos, res, _ = ref_inf.infercnv(adata, inplace=False, n_jobs=1, **kw)
+    chr_pos, res, per_gene = ref_inf.infercnv(
+        adata, inplace=False, n_jobs=1, calculate_gene_values=bool(case.get("gene_values")), **kw
+    )
     res = sp.csr_matrix(res)
     out = {
         "x_sha256": np.array(checksum(X)),
@@ -55,6 +58,8 @@ def run_reference(case):
         "indptr": res.indptr.astype(np.int64),
         "shape": np.array(res.shape, dtype=np.int64),
     }
+    if case.get("gene_values"):
+        out["per_gene"] = np.asarray(per_gene, dtype=np.float64)  # [n, n_var], NaN = not covered / masked
     if case.get("score_labels") is not None:
         rng = np.random.default_rng(case["score_labels"])
         labels = rng.integers(0, 4, size=X.shape[0]).astype(str)
@@ -70,7 +75,10 @@ def run_reference(case):
 def main():
     if not ref_loader.available():
         raise SystemExit("reference not present; goldens can only be regenerated in the build container")
+    only = set(sys.argv[1:])
     for case in CASES:
+        if only and case["name"] not in only:
+            continue
         out = run_reference(case)
         path = HERE / f"{case['name']}.npz"
         np.savez_compressed(path, **out)

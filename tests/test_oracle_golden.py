@@ -108,26 +108,77 @@ def test_cnv_score_known_answer():
         assert res["B"] == pytest.approx(2.5, abs=1e-3)
 
 
+# ---- per-gene layer (calculate_gene_values=True): the reference's own known answers ------------------
+def test_gene_values_window_smaller_than_segment():
+    # /root/reference/tests/test_tools.py:64-89
+    x = np.array([[1, 2, 3, 4, 5], [6, 7, 8, 9, 10]])
+    pos, vals = orc.gene_values_for_segment(orc.running_mean(x, 3, 1), 5, 3, 1)
+    np.testing.assert_array_equal(pos, np.arange(5))
+    np.testing.assert_array_equal(vals, np.array([[2.0, 2.5, 3.0, 3.5, 4.0], [7.0, 7.5, 8.0, 8.5, 9.0]]))
+
+
+def test_gene_values_window_larger_than_segment():
+    # /root/reference/tests/test_tools.py:92-117
+    x = np.array([[1, 2, 3, 4, 5], [6, 7, 8, 9, 10]])
+    pos, vals = orc.gene_values_for_segment(orc.running_mean(x, 7, 1), 5, 7, 1)
+    np.testing.assert_array_equal(pos, np.arange(5))
+    np.testing.assert_array_equal(vals, np.array([[3.0] * 5, [8.0] * 5]))
+
+
+def test_gene_averages_known_answer():
+    # /root/reference/tests/test_tools.py:120-140: three windows of three genes over five genes
+    smoothed = np.array([[2, 3, 4], [4, 4, 6], [6, 2, 1]], dtype=np.float64)
+    pos, vals = orc.gene_values_for_segment(smoothed, 5, 3, 1)
+    want = np.array([[2.0, 2.5, 3.0, 3.5, 4.0], [4.0, 4.0, 14 / 3, 5.0, 6.0], [6.0, 4.0, 3.0, 1.5, 1.0]])
+    np.testing.assert_allclose(vals, want, rtol=1e-15)
+
+
+def test_chunk_with_gene_values_known_answer(full_mock, x_res_actual, gene_res_actual):
+    # /root/reference/tests/test_tools.py:143-155
+    X, var = full_mock
+    ref = orc.reference_profile(X)
+    chr_pos, res, (cols, gene_res) = orc.infercnv_chunk(
+        X, var["chromosome"].values, var["start"].values, ref, 1, 3, 1, 1, gene_values=True
+    )
+    np.testing.assert_array_equal(res.toarray(), x_res_actual)
+    np.testing.assert_array_equal(cols, np.arange(10))
+    np.testing.assert_allclose(gene_res, gene_res_actual, rtol=1e-8)
+    assert {k: int(v) for k, v in chr_pos.items()} == {"chr1": 0, "chr2": 3}
+
+
+def test_public_with_gene_values_known_answer(full_mock, x_res_actual):
+    # /root/reference/tests/test_tools.py:172-191 (two chunks of two cells)
+    X, var = full_mock
+    chr_pos, res, per_gene = orc.infercnv(
+        X, var["chromosome"].values, var["start"].values, chunksize=2, lfc_clip=1, window_size=3, step=1,
+        dynamic_threshold=1, calculate_gene_values=True,
+    )
+    np.testing.assert_array_equal(per_gene[0], np.array([0.75, 0.0, 0.0, 0.0, -0.75, 0.0, 0.0, 0.0, 0.0, 0.75]))
+    np.testing.assert_array_equal(per_gene[3], np.array([0, 0, 0, 0, 0, 0.921875, 0.703125, 0, 0, 0]))
+    np.testing.assert_array_equal(res.toarray(), x_res_actual)
+
+
 # ---- outputs of the real reference, generated by tests/golden/make_golden.py ----------------------
 def _run_oracle(case):
     X, var, obs, kw = build_case(case)
     kw = dict(kw)
     key = kw.pop("reference_key", None)
     Xin = sp.csr_matrix(X) if case.get("container") == "csr" else X
-    chr_pos, res = orc.infercnv(
+    out = orc.infercnv(
         Xin,
         var["chromosome"].values,
         var["start"].values,
         obs_column=None if key is None else obs[key].values,
+        calculate_gene_values=bool(case.get("gene_values")),
         **kw,
     )
-    return X, chr_pos, res
+    return (X, *out) if case.get("gene_values") else (X, *out, None)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_oracle_matches_reference_golden(case, golden_loader):
     gold = golden_loader(case["name"])
-    X, chr_pos, res = _run_oracle(case)
+    X, chr_pos, res, per_gene = _run_oracle(case)
     assert hashlib.sha256(np.ascontiguousarray(X).tobytes()).hexdigest() == str(gold["x_sha256"]), "RNG stream drifted"
     assert {k: int(v) for k, v in chr_pos.items()} == gold["chr_pos"]
     assert list(chr_pos.keys()) == list(gold["chr_pos"].keys())
@@ -137,6 +188,11 @@ def test_oracle_matches_reference_golden(case, golden_loader):
     np.testing.assert_array_equal(res.indices, gold["csr"].indices)
     np.testing.assert_array_equal(res.data, gold["csr"].data)
     assert res.dtype == np.float64
+    if case.get("gene_values"):
+        want = gold["per_gene"]
+        assert per_gene.shape == want.shape
+        np.testing.assert_array_equal(np.isnan(per_gene), np.isnan(want))
+        np.testing.assert_array_equal(np.nan_to_num(per_gene), np.nan_to_num(want))  # bit-identical float64
 
 
 def test_oracle_cnv_score_golden(golden_loader):
