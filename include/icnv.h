@@ -119,6 +119,16 @@ int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t 
                          int64_t chunk_rows, const double* thr, double* row_abs_sum, int32_t* row_nnz,
                          void* stream);
 
+/* Per-gene layer of calculate_gene_values=True, tl/_infercnv.py:141-151, :214-223, :238-242, :247-291, :443-444, :452-453.
+ * From the smoothed rows in `tmp` (icnv_smooth_*): value(gene) = np.mean (numpy's pairwise order) of the kept windows that
+ * contain the gene (:278-287; the flat mean on chromosomes not longer than the window, :240), minus the median of the
+ * row's covered genes (:444), zeroed where |v| < thr[chunk of row] (the WINDOW matrix's threshold, :453; thr == NULL:
+ * no filter).  gene_out [n_rows, ldg >= n_genes] float64 in the matrix's own column order; genes no kept window
+ * covers and genes outside the plan's chromosomes are NaN (:146).  icnv_plan_gene_coverage: number of non-NaN columns. */
+int icnv_gene_values(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t ld_tmp, int64_t chunk_rows,
+                     const double* thr, double* gene_out, int64_t ldg, void* stream);
+int icnv_plan_gene_coverage(const icnv_plan* plan, int32_t* n_covered);
+
 /* Dense [n_rows, K] -> CSR (tl/_infercnv.py:455).  indptr [n_rows+1] int64 must
  * already hold the exclusive prefix sum of row_nnz; indices int32; data float32
  * or float64 following out_is_f64. */

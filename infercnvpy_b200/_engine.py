@@ -203,6 +203,34 @@ class DevicePlan:
             )
         return thr, row_abs, row_nnz
 
+    def gene_values(self, tmp, chunk_rows: int, thr=None, out=None):
+        """Per-gene layer of ``calculate_gene_values=True`` for the rows of ``tmp`` (output of :meth:`smooth`):
+        ``[n, n_genes]`` float64 in the matrix's column order, NaN where no kept window covers the gene.
+        ``thr``: the per-chunk thresholds :meth:`threshold` returned (``None`` = no noise filter)."""
+        torch = _torch()
+        n = tmp.shape[0]
+        G = self.layout.n_genes
+        if out is None:
+            out = torch.empty((n, G), dtype=torch.float64, device=self.device)
+        assert out.dtype == torch.float64 and out.stride(1) == 1
+        if self.K == 0:  # no chromosome takes part: nothing is covered
+            out.fill_(float("nan"))
+        elif n:
+            _lib.check(
+                self.lib.icnv_gene_values(
+                    self.handle, _lib.ptr(tmp), n, tmp.stride(0), int(chunk_rows), _lib.ptr(thr), _lib.ptr(out), out.stride(0),
+                    self._stream(),
+                ),
+                "icnv_gene_values",
+            )
+        return out
+
+    @property
+    def n_covered(self) -> int:
+        v = C.c_int32()
+        _lib.check(self.lib.icnv_plan_gene_coverage(self.handle, C.byref(v)), "icnv_plan_gene_coverage")
+        return int(v.value)
+
     def to_csr(self, out, row_nnz):
         """Dense thresholded block -> device CSR ``(indptr int64, indices int32, data)``."""
         torch = _torch()

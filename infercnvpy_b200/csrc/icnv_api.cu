@@ -107,6 +107,11 @@ struct icnv_plan {
     // ---- workspace for column sums
     DevBuf<double> colsum_partial;
 
+    // ---- per-gene layer (calculate_gene_values=True): coverage of every position-sorted gene by the kept windows
+    int32_t n_cov = 0;
+    DevBuf<int32_t> gv_first, gv_cnt, gv_inv, gv_kaddr;
+    DevBuf<double> gv_scratch;
+
     ~icnv_plan() {
         off_w.release();
         cols_w.release();
@@ -124,6 +129,11 @@ struct icnv_plan {
         tasks_d.release();
         flat_inv.release();
         colsum_partial.release();
+        gv_first.release();
+        gv_cnt.release();
+        gv_inv.release();
+        gv_kaddr.release();
+        gv_scratch.release();
     }
 };
 
@@ -404,6 +414,35 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
     if (p->flat_inv.upload(flat_inv)) return ICNV_ECUDA;
     if (p->lo_lin.alloc((size_t)(n_sorted + 4) * 8) || p->hi_lin.alloc((size_t)(n_sorted + 4) * 8)) return ICNV_ECUDA;
 
+    // ---- per-gene layer tables (tl/_infercnv.py:214-223, :238-242, :278-287): the gene at sorted position pos of a
+    // regular chromosome lies in the kept windows k with k*step <= pos < k*step + window; every gene of a flat
+    // chromosome takes its single column.  Task index -> tile-order address is the same for both task lists.
+    {
+        std::vector<int32_t> first, cnt, inv(n_genes, -1), kaddr((size_t)p->K, 0);
+        int32_t ti = 0;
+        for (int c = 0; c < n_seg; ++c) {
+            const int32_t s0 = p->seg_off[c];
+            const int32_t Gc = p->seg_off[c + 1] - s0;
+            const int64_t no = n_out[c];
+            for (int64_t t = 0; t * LOUT < no; ++t, ++ti)
+                for (int64_t i = 0; i < std::min<int64_t>(LOUT, no - t * LOUT); ++i)
+                    kaddr[(size_t)(p->out_off[c] + t * LOUT + i)] = (ti / 32) * (32 * LOUT) + (int32_t)i * 32 + (ti % 32);
+            for (int32_t pos = 0; pos < Gc; ++pos) {
+                int64_t k_lo = 0, k_hi = 0;
+                if (!is_flat[c]) {
+                    k_lo = pos - n + 1 <= 0 ? 0 : (pos - n + 1 + s - 1) / s;
+                    k_hi = std::min<int64_t>(no - 1, pos / s);
+                    if (k_lo > k_hi) continue;
+                }
+                inv[p->gene_idx[s0 + pos]] = (int32_t)first.size();
+                first.push_back((int32_t)(p->out_off[c] + k_lo));
+                cnt.push_back((int32_t)(k_hi - k_lo + 1));
+            }
+        }
+        p->n_cov = (int32_t)first.size();
+        if (p->gv_first.upload(first) || p->gv_cnt.upload(cnt) || p->gv_inv.upload(inv) || p->gv_kaddr.upload(kaddr)) return ICNV_ECUDA;
+    }
+
     Choice ch;
     p->base_tier = choose(*p, false, &ch) == 0 ? ch.tier : -1;
     *out = p.release();
@@ -649,6 +688,67 @@ int icnv_center_rows(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t
         return ICNV_EINVAL;
     }
     return aux_center_rows(tmp, n_rows, ld_tmp, tasks, n_tasks, (int)plan->K, out, out_is_f64 != 0, ldo, row_stats, (cudaStream_t)stream);
+}
+
+int icnv_gene_values(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t ld_tmp, int64_t chunk_rows, const double* thr,
+                     double* gene_out, int64_t ldg, void* stream) {
+    if (!plan || !tmp || !gene_out || chunk_rows < 1 || ldg < plan->G || n_rows < 0) {
+        set_error("icnv_gene_values: bad argument");
+        return ICNV_EINVAL;
+    }
+    if (n_rows == 0) return ICNV_OK;
+    Choice ch;
+    int rc = choose(*plan, plan->c64, &ch);
+    if (rc) return rc;
+    const int n_tasks = ch.tier < 2 ? plan->n_tasks_g : plan->n_tasks_d;
+    if (ld_tmp < (int64_t)((n_tasks + 31) / 32) * (32 * LOUT + 1)) {
+        set_error("icnv_gene_values: intermediate pitch smaller than icnv_plan_tmp_width");
+        return ICNV_EINVAL;
+    }
+    GeneValParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.tmp = tmp;
+    gp.n_rows = n_rows;
+    gp.ld = ld_tmp;
+    gp.kaddr = plan->gv_kaddr.ptr;
+    gp.K = (int32_t)plan->K;
+    gp.first = plan->gv_first.ptr;
+    gp.cnt = plan->gv_cnt.ptr;
+    gp.n_cov = plan->n_cov;
+    gp.inv = plan->gv_inv.ptr;
+    gp.G = plan->G;
+    gp.chunk_rows = chunk_rows;
+    gp.thr = thr;
+    gp.out = gene_out;
+    gp.ldo = ldg;
+    // shared memory: window values first (small), then the per-gene means if they still fit
+    const size_t budget = SMEM_MAX - 4096;
+    size_t smem = 0;
+    if ((size_t)plan->K * 8 <= budget) {
+        gp.k_in_smem = 1;
+        smem += (size_t)plan->K * 8;
+    }
+    if (smem + (size_t)plan->n_cov * 8 <= budget) {
+        gp.v_in_smem = 1;
+        smem += (size_t)plan->n_cov * 8;
+    }
+    const int grid = (int)std::min<int64_t>(n_rows, (int64_t)plan->n_sm);  // 118 registers x 512 threads: one CTA per SM
+    if (!gp.v_in_smem) {
+        const size_t need = (size_t)grid * std::max(plan->n_cov, 1);
+        if (plan->gv_scratch.n < need) {
+            ICNV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // an earlier launch may still use the old buffer
+            plan->gv_scratch.release();
+            if (plan->gv_scratch.alloc(need)) return ICNV_ECUDA;
+        }
+        gp.scratch = plan->gv_scratch.ptr;
+    }
+    return genevals_launch(gp, grid, smem < 16 ? 16 : smem, (cudaStream_t)stream);
+}
+
+int icnv_plan_gene_coverage(const icnv_plan* plan, int32_t* n_covered) {
+    if (!plan || !n_covered) return ICNV_EINVAL;
+    *n_covered = plan->n_cov;
+    return ICNV_OK;
 }
 
 int icnv_chunk_threshold(const double* row_stats, int64_t n_rows, int64_t K, int64_t chunk_rows, double dyn_thr, double* thr,

@@ -84,6 +84,25 @@ struct SmoothParams {
     int32_t dbg_rows;
 };
 
+// per-gene layer (icnv_genevals.cu)
+struct GeneValParams {
+    const double* tmp;       // [n_rows, ld] smoothing kernel output (tile order)
+    int64_t n_rows, ld;
+    const int32_t* kaddr;    // [K] position of output column k inside a tmp row
+    int32_t K;
+    const int32_t* first;    // [n_cov] first window column of the covered gene (position order)
+    const int32_t* cnt;      // [n_cov] number of windows covering it
+    int32_t n_cov;
+    const int32_t* inv;      // [G] natural column -> covered index, -1 = NaN
+    int32_t G;
+    int64_t chunk_rows;
+    const double* thr;       // [n_chunks] or nullptr (dynamic_threshold=None)
+    double* scratch;         // [grid, n_cov] when the means do not fit in shared memory, else nullptr
+    double* out;             // [n_rows, ldo] float64
+    int64_t ldo;
+    int32_t k_in_smem, v_in_smem;
+};
+
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,5 +171,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, const SmoothParams& p, int grid,
                   size_t smem, cudaStream_t stream);
 int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, size_t smem, int* ctas_per_sm);
+
+int genevals_launch(const GeneValParams& p, int grid, size_t smem, cudaStream_t st);
 
 }  // namespace icnv

@@ -19,11 +19,11 @@ from .._layout import build_layout
 log = logging.getLogger("infercnvpy_b200")
 
 
-def _block_rows(n_rows: int, n_genes: int, n_out: int, chunksize: int) -> int:
+def _block_rows(n_rows: int, n_genes: int, n_out: int, chunksize: int, gene_values: bool = False) -> int:
     """Rows per device block: a multiple of ``chunksize`` (so every per-chunk std sees a whole
     chunk, _infercnv.py:123,450) that keeps input + output under ICNV_BLOCK_BYTES (default 16 GiB)."""
     budget = int(os.environ.get("ICNV_BLOCK_BYTES", 16 << 30))
-    per_row = 4 * n_genes + 14 * n_out + 64
+    per_row = 4 * n_genes + 14 * n_out + 64 + (8 * n_genes + 10 * n_out if gene_values else 0)
     chunks = max(1, (budget // per_row) // chunksize)
     return min(n_rows, chunks * chunksize) if n_rows else 0
 
@@ -181,6 +181,36 @@ def _to_host(t):
     return out.reshape(t.shape)
 
 
+def _to_host_into(t, dst: np.ndarray, slab_bytes: int = 256 << 20):
+    """Device matrix -> rows of a preallocated C-contiguous numpy array, in row slabs through two pinned buffers
+    (the DMA of slab i+1 overlaps the host copy of slab i)."""
+    import torch
+
+    n, w = t.shape
+    assert dst.shape == (n, w) and dst.flags.c_contiguous and dst.dtype == np.dtype(str(t.dtype).replace("torch.", ""))
+    if n == 0:
+        return
+    rows = max(1, slab_bytes // max(1, w * t.element_size()))
+    bufs = [torch.empty((min(rows, n), w), dtype=t.dtype, pin_memory=True) for _ in range(2 if n > rows else 1)]
+    evs = [None] * len(bufs)
+    spans = [(a, min(n, a + rows)) for a in range(0, n, rows)]
+
+    def issue(i):
+        a, b = spans[i]
+        bufs[i % len(bufs)][: b - a].copy_(t[a:b], non_blocking=True)
+        evs[i % len(bufs)] = torch.cuda.Event()
+        evs[i % len(bufs)].record()
+
+    issue(0)
+    for i, (a, b) in enumerate(spans):
+        evs[i % len(bufs)].synchronize()
+        if i + 1 < len(spans) and len(bufs) > 1:
+            issue(i + 1)
+        np.copyto(dst[a:b], bufs[i % len(bufs)][: b - a].numpy())
+        if i + 1 < len(spans) and len(bufs) == 1:
+            issue(i + 1)
+
+
 def _host_csr(indptr, indices, data, shape):
     """Device CSR pieces -> scipy CSR float64 (the reference's container, _infercnv.py:455); the float64
     widening happens on the device so the host never touches the values."""
@@ -286,10 +316,6 @@ def infercnv(
     layout, plan = _cached_plan(adata.var, window_size, step, exclude_chromosomes, device)
     if layout.n_null:
         log.warning(f"Skipped {layout.n_null} genes because they don't have a genomic position annotated. ")
-    if calculate_gene_values:
-        raise NotImplementedError(
-            "calculate_gene_values=True (per-gene CNV layer, _infercnv.py:141-151) is not built yet; see DESIGN.md"
-        )
     chunksize = int(chunksize)
     if chunksize < 1:
         raise ValueError("chunksize must be positive")
@@ -318,7 +344,7 @@ def infercnv(
 
     if True:
         K = plan.K
-        block = _block_rows(n_rows, n_genes, K, chunksize)
+        block = _block_rows(n_rows, n_genes, K, chunksize, calculate_gene_values)
         blocks = [(r0, min(n_rows, r0 + block)) for r0 in range(0, n_rows, max(block, 1))]
         resident = None
         need_sums = ref_host is None
@@ -371,14 +397,21 @@ def infercnv(
 
         # ---- smoothing, noise filter, CSR (blocks are multiples of chunksize)
         parts = []
+        # per-gene layer (_infercnv.py:141-148): dense float64 [n_obs, n_vars], NaN for genes without a value
+        per_gene = np.empty((n_rows, n_genes), dtype=np.float64) if calculate_gene_values else None
         for r0, r1 in blocks:
             Xb = resident if resident is not None else _rows_to_device(expr, r0, r1, device)
             if isinstance(Xb, tuple) and plan.tier == 2:
                 Xb = _densify(Xb, n_genes, device)
             tmp = plan.smooth(Xb, lfc_clip)
             out, stats = plan.center(tmp)
+            thr, _, row_nnz = plan.threshold(out, stats, chunksize, dynamic_threshold)
+            if calculate_gene_values:
+                # own row median (:444), the window matrix's chunk thresholds (:453); copied out in row slabs
+                gv = plan.gene_values(tmp, chunksize, thr)
+                _to_host_into(gv, per_gene[r0:r1])
+                del gv
             del tmp
-            _, _, row_nnz = plan.threshold(out, stats, chunksize, dynamic_threshold)
             indptr, indices, data = plan.to_csr(out, row_nnz)
             parts.append(_host_csr(indptr, indices, data, (r1 - r0, K)))
             del out, stats, Xb
@@ -391,17 +424,7 @@ def infercnv(
     if inplace:
         adata.obsm[f"X_{key_added}"] = res
         adata.uns[key_added] = {"chr_pos": chr_pos}
+        if calculate_gene_values:
+            adata.layers[f"gene_values_{key_added}"] = per_gene
     else:
-        return chr_pos, res, None
-
-
-def _densify(csr_triple, n_genes, device):
-    """CSR block -> dense float32 block for the direct-form kernel (rare (window, step) pairs)."""
-    import torch
-
-    indptr, indices, data = csr_triple
-    n = indptr.numel() - 1
-    dense = torch.zeros((n, n_genes), dtype=torch.float32, device=device)
-    rows = torch.repeat_interleave(torch.arange(n, device=device), (indptr[1:] - indptr[:-1]))
-    dense[rows, indices.long()] = data
-    return dense
+        return chr_pos, res, per_gene

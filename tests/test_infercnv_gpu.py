@@ -70,6 +70,120 @@ def test_public_api_matches_reference_golden(case, golden_loader):
     _compare_thresholded(res.toarray(), gold["csr"].toarray(), kw.get("chunksize", 5000), what=case["name"])
 
 
+GV_CASES = [c for c in CASES if c.get("gene_values")]
+
+
+def _compare_gene_layer(got, want, chunk, what):
+    assert got.shape == want.shape and got.dtype == np.float64
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want), err_msg=what)  # same genes covered (:146)
+    g, w = np.nan_to_num(got), np.nan_to_num(want)
+    both = (g != 0) & (w != 0)
+    # float64 end to end: window sums differ from np.convolve only in summation order
+    np.testing.assert_allclose(g[both], w[both], rtol=1e-9, atol=1e-13, err_msg=what)
+    return _compare_thresholded(g, w, chunk, rtol=1e-6, what=what)
+
+
+@pytest.mark.parametrize("case", GV_CASES, ids=[c["name"] for c in GV_CASES])
+def test_gene_values_match_reference_golden(case, golden_loader):
+    """calculate_gene_values=True (_infercnv.py:141-151, :247-291, :443-444, :452-453) == the real reference's layer."""
+    gold = golden_loader(case["name"])
+    X, var, obs, kw = build_case(case)
+    kw = {k: v for k, v in kw.items() if k not in ("reference_key", "reference_cat", "reference")}
+    adata = _adata(X, var, obs)
+    chr_pos, res, per_gene = cnv.tl.infercnv(
+        adata, reference=gold["profile"], inplace=False, calculate_gene_values=True, **kw
+    )
+    assert {k: int(v) for k, v in chr_pos.items()} == gold["chr_pos"]
+    chunk = kw.get("chunksize", 5000)
+    _compare_thresholded(res.toarray(), gold["csr"].toarray(), chunk, what=case["name"])
+    _compare_gene_layer(per_gene, gold["per_gene"], chunk, case["name"])
+    # inplace key (:157-158)
+    cnv.tl.infercnv(adata, reference=gold["profile"], calculate_gene_values=True, key_added="k2", **kw)
+    np.testing.assert_array_equal(np.nan_to_num(adata.layers["gene_values_k2"]), np.nan_to_num(per_gene))
+
+
+def test_gene_values_reference_known_answers(full_mock, x_res_actual, gene_res_actual):
+    """/root/reference/tests/test_tools.py:143-191 with the per-gene rows (conftest.py:78-95)."""
+    X, var = full_mock
+    adata = _adata(sp.csr_matrix(X), var)
+    chr_pos, res, per_gene = cnv.tl.infercnv(
+        adata, chunksize=2, lfc_clip=1, window_size=3, step=1, dynamic_threshold=1, inplace=False,
+        calculate_gene_values=True,
+    )
+    np.testing.assert_allclose(res.toarray(), x_res_actual, rtol=1e-6, atol=0)
+    # test_tools.py:185-191 pins rows 0 and 3 of the two-chunk run
+    np.testing.assert_allclose(per_gene[0], [0.75, 0.0, 0.0, 0.0, -0.75, 0.0, 0.0, 0.0, 0.0, 0.75], rtol=1e-12)
+    np.testing.assert_allclose(per_gene[3], [0, 0, 0, 0, 0, 0.921875, 0.703125, 0, 0, 0], rtol=1e-12)
+    # one chunk of four cells == conftest's gene_res_actual (test_tools.py:143-169)
+    _, _, per_gene1 = cnv.tl.infercnv(
+        adata, chunksize=5000, lfc_clip=1, window_size=3, step=1, dynamic_threshold=1, inplace=False,
+        calculate_gene_values=True,
+    )
+    np.testing.assert_allclose(per_gene1, gene_res_actual, rtol=1e-8)
+
+
+@pytest.mark.parametrize("g,window,step", [(30000, 100, 10), (20000, 250, 10), (3000, 20, 3), (6000, 260, 1)])
+def test_gene_values_match_oracle_other_shapes(g, window, step):
+    """30000 genes: the per-gene means no longer fit in shared memory (L2 scratch path); window 260 / step 1: every
+    gene sits in up to 260 windows, i.e. numpy's pairwise recursion beyond one block of 128."""
+    n = 6
+    var = cnv.datasets.synthetic_var(g, seed=5, with_extras=True)
+    X = cnv.datasets.synthetic_counts(n, g, seed=g + window + step)
+    ref = X.mean(axis=0, dtype=np.float64).astype(np.float32)
+    adata = _adata(X, var)
+    chr_pos, res, per_gene = cnv.tl.infercnv(
+        adata, reference=ref, window_size=window, step=step, chunksize=4, inplace=False, calculate_gene_values=True
+    )
+    _, want_res, want_gene = orc.infercnv(
+        X, var["chromosome"].values, var["start"].values, reference=ref, window_size=window, step=step, chunksize=4,
+        calculate_gene_values=True,
+    )
+    _compare_thresholded(res.toarray(), want_res.toarray(), 4, what="windows")
+    _compare_gene_layer(per_gene, want_gene, 4, f"g={g} window={window} step={step}")
+
+
+def test_gene_values_properties_at_scale():
+    """Bench-shaped gene axis, a few thousand cells: size-independent properties of the layer."""
+    torch = _torch()
+    from infercnvpy_b200._engine import DevicePlan
+    from infercnvpy_b200._layout import build_layout
+
+    dev = torch.device("cuda", 0)
+    G, N, chunk = 20000, 3000, 1000
+    var = cnv.datasets.synthetic_var(G, seed=0)
+    Xd = cnv.datasets.device_counts(N, G, dev, seed=77)
+    layout = build_layout(var, 100, 10)
+    with DevicePlan(layout, dev) as plan:
+        sums, counts = plan.colsum(Xd)
+        plan.set_reference(plan.mean_from_sums(sums, counts))
+        tmp = plan.smooth(Xd, 3.0)
+        out, stats = plan.center(tmp)
+        thr, _, _ = plan.threshold(out, stats, chunk, 1.5)
+        raw = plan.gene_values(tmp, chunk, None)
+        filt = plan.gene_values(tmp, chunk, thr)
+        n_cov = plan.n_covered
+        # (1) the same columns are NaN in every row, and exactly n_covered are not
+        nan = torch.isnan(raw)
+        assert torch.equal(nan, nan[0:1].expand_as(nan)) and int((~nan[0]).sum()) == n_cov
+        assert torch.equal(torch.isnan(filt), nan)
+        # (2) every row of the unfiltered layer has median 0 over its covered genes (np.median, even n: middle pair)
+        vals = raw[:, ~nan[0]]
+        srt = vals.sort(dim=1).values
+        mid = 0.5 * (srt[:, (n_cov - 1) // 2] + srt[:, n_cov // 2])
+        assert float(mid.abs().max()) < 1e-15
+        # (3) the filter zeroes exactly the entries below the row's chunk threshold and keeps the others unchanged
+        t_row = thr.repeat_interleave(chunk)[:N, None]
+        keep = vals.abs() >= t_row
+        assert torch.equal(filt[:, ~nan[0]], torch.where(keep, vals, torch.zeros_like(vals)))
+        # (4) a gene covered by exactly one window equals that window's pre-median value up to the two medians:
+        #     value - window is constant along the row for all such genes (first `step` genes of every chromosome)
+        pre = plan.center(tmp, out_dtype=torch.float64)[0]
+        first_gene = torch.from_numpy(layout.gene_idx[layout.seg_off[:-1]].astype(np.int64)).to(dev)
+        first_col = torch.from_numpy(np.asarray(layout.out_off[:-1], dtype=np.int64)).to(dev)
+        d = raw[:, first_gene] - pre[:, first_col]
+        assert float((d - d[:, :1]).abs().max()) < 1e-14
+
+
 @pytest.mark.parametrize("name", ["small_default", "small_cats", "small_onecat", "small_csr", "g20k_win100"])
 def test_data_derived_reference_profile(name, golden_loader):
     """Reference profile computed on the device (all cells / per category, dense and CSR)."""
