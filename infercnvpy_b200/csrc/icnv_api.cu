@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <memory>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -140,12 +141,15 @@ struct icnv_plan {
 namespace {
 
 constexpr size_t SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA on sm_100
+#ifndef ICNV_SMOOTH_ROWS_DEFAULT
+#define ICNV_SMOOTH_ROWS_DEFAULT 2
+#endif
 
-size_t smem_grouped(const icnv_plan& p, int tier) {
+size_t smem_grouped(const icnv_plan& p, int tier, int rows = 1) {
     size_t s = smooth_scratch_bytes();
-    s += (size_t)p.Gpad * 4;
-    s += (size_t)(p.NGpad + PAD_GROUPS) * 16;
-    if (p.qstar >= 0) s += (size_t)(p.NGpad + PAD_GROUPS) * 8;
+    s += (size_t)rows * p.Gpad * 4;
+    s += (size_t)rows * (p.NGpad + PAD_GROUPS) * 16;
+    if (p.qstar >= 0) s += (size_t)rows * (p.NGpad + PAD_GROUPS) * 8;
     if (tier == 1) s += (size_t)p.NQ * 16 + (size_t)p.gs * 8;
     return (s + 15) / 16 * 16;
 }
@@ -159,7 +163,18 @@ size_t smem_direct(const icnv_plan& p, bool c64) {
 struct Choice {
     int tier, nwin, gs, tpt;
     size_t smem;
+    int rows = 1;  // cell rows staged together per CTA iteration (icnv_smooth.cu, ROWS)
 };
+
+// Row pairs (ROWS = 2) exist for the templated window-100 kernel; ICNV_SMOOTH_ROWS=1|2 overrides the default.
+int smooth_rows_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("ICNV_SMOOTH_ROWS");
+        v = (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : ICNV_SMOOTH_ROWS_DEFAULT);
+    }
+    return v;
+}
 
 // which kernel instantiation runs for this plan + reference dtype
 int choose(const icnv_plan& p, bool c64, Choice* c) {
@@ -167,6 +182,10 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
         const bool templ = (p.step == 10 && (p.window == 100 || p.window == 250));
         if (templ && p.n_tasks_g <= NT && smem_grouped(p, 0) <= SMEM_MAX) {
             *c = {0, p.window, p.gs, 1, smem_grouped(p, 0)};
+            if (p.window == 100 && smooth_rows_default() == 2 && smem_grouped(p, 0, 2) <= SMEM_MAX) {
+                c->rows = 2;
+                c->smem = smem_grouped(p, 0, 2);
+            }
             return 0;
         }
         if (smem_grouped(p, 1) <= SMEM_MAX && p.n_tasks_g <= 4 * NT) {  // TPT 1 or 4
@@ -184,7 +203,7 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
                   std::to_string(4 * NT * LOUT));
         return ICNV_EUNSUPPORTED;
     }
-    *c = {2, 0, 0, p.n_tasks_d <= NT ? 1 : 4, smem_direct(p, c64)};
+    *c = {2, 0, 0, p.n_tasks_d <= NT ? 1 : 4, smem_direct(p, c64), 1};
     return 0;
 }
 
@@ -483,7 +502,7 @@ int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* thread
     int rc = choose(*plan, plan->c64, &ch);
     if (rc) return rc;
     int occ = 0;
-    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.smem, &occ);
+    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
     if (rc) return rc;
     if (ctas_per_sm) *ctas_per_sm = occ;
     if (threads) *threads = NT;
@@ -632,14 +651,14 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
     sp.dbg_rows = g_dbg_rows;
     sp.use_tma = sp.X && (sp.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp.X) & 15) == 0) && (plan->G % 4 == 0);
     int occ = 0;
-    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.smem, &occ);
+    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
     if (rc) return rc;
     if (occ < 1) {
         set_error("smooth: kernel does not fit on an SM");
         return ICNV_EUNSUPPORTED;
     }
-    const int grid = (int)std::min<int64_t>(sp.n_rows, (int64_t)plan->n_sm * occ);
-    return smooth_launch(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, sp, grid, ch.smem, (cudaStream_t)stream);
+    const int grid = (int)std::min<int64_t>((sp.n_rows + ch.rows - 1) / ch.rows, (int64_t)plan->n_sm * occ);
+    return smooth_launch(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, sp, grid, ch.smem, (cudaStream_t)stream);
 }
 
 int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip, double* tmp,

@@ -168,9 +168,9 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 // Launchers implemented in icnv_smooth.cu
-int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, const SmoothParams& p, int grid,
+int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, const SmoothParams& p, int grid,
                   size_t smem, cudaStream_t stream);
-int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, size_t smem, int* ctas_per_sm);
+int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm);
 
 int genevals_launch(const GeneValParams& p, int grid, size_t smem, cudaStream_t st);
 

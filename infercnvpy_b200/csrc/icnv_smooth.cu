@@ -41,8 +41,11 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT>
-__global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_kernel(const SmoothParams p) {
+// ROWS = cell rows staged and gathered together per CTA iteration (grouped tiers only).  ROWS == 2 reads every
+// gather-table entry once for two rows — the tables (160 KB per sweep, L2 -> L1) are the largest removable share of the
+// kernel's l1tex work — at the price of one CTA per SM (2 x 80 KB of staged rows + 2 x 32 KB of partials).
+template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS>
+__global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 : 1) smooth_kernel(const SmoothParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     Scratch* sc = reinterpret_cast<Scratch*>(smem);
     unsigned char* carve = smem + SCRATCH_BYTES;
@@ -60,6 +63,8 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     constexpr int QSTAR_C = M3_C ? (NWIN / 2) / GS : -1;
     static_assert(TIER != 0 || NWIN % 2 == 0, "tier 0 instantiations use even windows");
     constexpr int VPT = TPT * LOUT;
+    static_assert(ROWS == 1 || TIER < 2, "row pairs are a feature of the grouped tiers");
+#define ICNV_ABS (p.NGpad + PAD_GROUPS) /* partial-sum slots per staged row */
 
     // ---- carve shared memory
     float* raw = nullptr;
@@ -75,12 +80,12 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     const int qstar = (TIER == 0) ? QSTAR_C : p.qstar;
     if constexpr (GROUPED) {
         raw = reinterpret_cast<float*>(carve);
-        carve += (size_t)p.Gpad * 4;
+        carve += (size_t)ROWS * p.Gpad * 4;
         AB = reinterpret_cast<double2*>(carve);
-        carve += (size_t)(p.NGpad + PAD_GROUPS) * 16;
+        carve += (size_t)ROWS * ICNV_ABS * 16;
         if ((TIER == 0) ? M3_C : (p.qstar >= 0)) {
             Cp = reinterpret_cast<double*>(carve);
-            carve += (size_t)(p.NGpad + PAD_GROUPS) * 8;
+            carve += (size_t)ROWS * ICNV_ABS * 8;
         }
         if constexpr (TIER == 1) {
             w_alpha = reinterpret_cast<double*>(carve);
@@ -99,10 +104,13 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     // ---- one-time setup
     const bool dense = p.X != nullptr;
     if constexpr (GROUPED) {
-        for (int i = p.G + tid; i < p.Gpad; i += NT) raw[i] = 0.f;
-        for (int i = p.NG + tid; i < p.NGpad + PAD_GROUPS; i += NT) {
-            AB[i] = make_double2(0.0, 0.0);
-            if (Cp) Cp[i] = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) {
+            for (int i = p.G + tid; i < p.Gpad; i += NT) raw[rr * p.Gpad + i] = 0.f;
+            for (int i = p.NG + tid; i < ICNV_ABS; i += NT) {
+                AB[(ROWS > 1 ? rr * ICNV_ABS : 0) + i] = make_double2(0.0, 0.0);
+                if (Cp) Cp[(ROWS > 1 ? rr * ICNV_ABS : 0) + i] = 0.0;
+            }
         }
         if constexpr (TIER == 1) {
             for (int i = tid; i < NQ; i += NT) {
@@ -128,15 +136,20 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
     const uint64_t pol = l2_policy_evict_first();
     uint32_t parity = 0;
     const uint32_t row_bytes = (uint32_t)p.G * 4u;
+#define ICNV_ROW_OFF ((uint32_t)p.Gpad * 4u) /* byte distance between the staged rows of a pair */
     auto issue_row = [&](int64_t r) {
-        const char* src = reinterpret_cast<const char*>(p.X + r * p.ldx);
-        mbar_expect_tx(&sc->mbar, row_bytes);
+        const int nvalid = (int)min((int64_t)ROWS, p.n_rows - r);
+        mbar_expect_tx(&sc->mbar, row_bytes * (uint32_t)nvalid);
         constexpr uint32_t CH = 16384;
-        for (uint32_t off = 0; off < row_bytes; off += CH)
-            bulk_g2s(reinterpret_cast<char*>(raw) + off, src + off, min(CH, row_bytes - off), &sc->mbar, pol);
+        for (int rr = 0; rr < nvalid; ++rr) {
+            const char* src = reinterpret_cast<const char*>(p.X + (r + rr) * p.ldx);
+            char* dst = reinterpret_cast<char*>(raw) + (size_t)rr * ICNV_ROW_OFF;
+            for (uint32_t off = 0; off < row_bytes; off += CH)
+                bulk_g2s(dst + off, src + off, min(CH, row_bytes - off), &sc->mbar, pol);
+        }
     };
 
-    int64_t row = blockIdx.x;
+    int64_t row = (int64_t)blockIdx.x * ROWS;  // first row of this iteration's group of ROWS
     const bool tma = GROUPED && dense && p.use_tma;
     if (tma && tid == ISSUER && row < p.n_rows) issue_row(row);
 
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
             p.dbg[((size_t)blockIdx.x * p.dbg_rows + it) * 16 + (slot)] = clock64();                       \
     } while (0)
 
-    for (; row < p.n_rows; row += gridDim.x, ++it) {
+    for (; row < p.n_rows; row += (int64_t)gridDim.x * ROWS, ++it) {
         ICNV_STAMP(0);
         // ======================= stage the raw row =======================
         if constexpr (GROUPED) {
@@ -170,17 +183,21 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 mbar_wait(&sc->mbar, parity);
                 parity ^= 1u;
                 ICNV_STAMP(1);
-                    } else if (dense) {
-                const float* src = p.X + row * p.ldx;
-                for (int i = tid; i < p.G; i += NT) raw[i] = __ldg(src + i);
+            } else if (dense) {
+                for (int rr = 0; rr < ROWS && row + rr < p.n_rows; ++rr) {
+                    const float* src = p.X + (row + rr) * p.ldx;
+                    for (int i = tid; i < p.G; i += NT) raw[rr * p.Gpad + i] = __ldg(src + i);
+                }
                 __syncthreads();
             } else {
                 // CSR: densify on load (the reference densifies too, _infercnv.py:423)
                 float4* r4 = reinterpret_cast<float4*>(raw);
-                for (int i = tid; i < (p.Gpad >> 2); i += NT) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = tid; i < ROWS * (p.Gpad >> 2); i += NT) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncthreads();
-                const int64_t e0 = p.indptr[row], e1 = p.indptr[row + 1];
-                for (int64_t e = e0 + tid; e < e1; e += NT) raw[__ldg(p.indices + e)] = __ldg(p.data + e);
+                for (int rr = 0; rr < ROWS && row + rr < p.n_rows; ++rr) {
+                    const int64_t e0 = p.indptr[row + rr], e1 = p.indptr[row + rr + 1];
+                    for (int64_t e = e0 + tid; e < e1; e += NT) raw[rr * p.Gpad + __ldg(p.indices + e)] = __ldg(p.data + e);
+                }
                 __syncthreads();
             }
         }
@@ -196,7 +213,11 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 wb = __shfl_sync(0xffffffffu, wb, 0);
                 if (wb >= n_wb) break;
                 const int quad = (wb << 5) + lane;  // slot index; every slot of every warp-block is valid
-                double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+                double a[ROWS][4], b[ROWS][4], c[ROWS][4];
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[rr][u] = b[rr][u] = c[rr][u] = 0.0;
                 // table entry (wb, j, lane, u): ((wb*gs + j)*32 + lane)*4 + u
                 const size_t tbase = ((size_t)wb * gs * 32 + lane) * 4;
                 const uint32_t* ip = p.off_w + tbase;
@@ -207,23 +228,35 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                     const float4 lo = ldg_nc_f4(lp + j * 128);
                     float4 hi = lo;
                     if constexpr (BOUNDED) hi = ldg_nc_f4(hp + j * 128);
-                    // table entries are complete shared-window addresses (raw base baked in by the host)
-                    const float x[4] = {lds_f32(id.x), lds_f32(id.y), lds_f32(id.z), lds_f32(id.w)};
+                    // table entries are complete shared-window addresses (raw base baked in by the host); the second
+                    // row of a pair sits row_off bytes further
                     const float l4[4] = {lo.x, lo.y, lo.z, lo.w};
                     const float h4[4] = {hi.x, hi.y, hi.z, hi.w};
+                    float x[ROWS][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float d;
-                        if constexpr (BOUNDED)
-                            d = x[u] > h4[u] ? x[u] - h4[u] : (x[u] < l4[u] ? x[u] - l4[u] : 0.f);
-                        else
-                            d = x[u] - l4[u];
-                        d = fminf(fmaxf(d, -clipf), clipf);
-                        const double dd = (double)d;
-                        a[u] += dd;
-                        if (j > 0) b[u] = fma((double)j, dd, b[u]);
-                        if (qstar >= 0) c[u] = fma(cwj, dd, c[u]);
+                    for (int rr = 0; rr < ROWS; ++rr) {
+                        const uint32_t ro = rr ? ICNV_ROW_OFF : 0u;
+                        x[rr][0] = lds_f32(id.x + ro);
+                        x[rr][1] = lds_f32(id.y + ro);
+                        x[rr][2] = lds_f32(id.z + ro);
+                        x[rr][3] = lds_f32(id.w + ro);
                     }
+#pragma unroll
+                    for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float xv = x[rr][u];
+                            float d;
+                            if constexpr (BOUNDED)
+                                d = xv > h4[u] ? xv - h4[u] : (xv < l4[u] ? xv - l4[u] : 0.f);
+                            else
+                                d = xv - l4[u];
+                            d = fminf(fmaxf(d, -clipf), clipf);
+                            const double dd = (double)d;
+                            a[rr][u] += dd;
+                            if (j > 0) b[rr][u] = fma((double)j, dd, b[rr][u]);
+                            if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
+                        }
                 };
                 if constexpr (TIER == 0) {
 #pragma unroll
@@ -235,17 +268,19 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 const int4 gid = __ldg(reinterpret_cast<const int4*>(p.grp_w) + quad);
                 const int gq[4] = {gid.x, gid.y, gid.z, gid.w};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    AB[gq[u]] = make_double2(a[u], b[u]);
-                    if (qstar >= 0) Cp[gq[u]] = c[u];
-                }
+                for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        AB[(ROWS > 1 ? rr * ICNV_ABS : 0) + gq[u]] = make_double2(a[rr][u], b[rr][u]);
+                        if (qstar >= 0) Cp[(ROWS > 1 ? rr * ICNV_ABS : 0) + gq[u]] = c[rr][u];
+                    }
             }
             ICNV_STAMP(2);
                 __syncthreads();  // gathers done: raw row is dead, partials visible
             ICNV_STAMP(3);
                 if (tid == ISSUER) {
                 *next_wb = 0;  // used again two rows from now
-                if (tma && row + gridDim.x < p.n_rows) issue_row(row + gridDim.x);
+                if (tma && row + (int64_t)gridDim.x * ROWS < p.n_rows) issue_row(row + (int64_t)gridDim.x * ROWS);
             }
             ICNV_STAMP(13);
         } else {
@@ -286,6 +321,11 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 continue;
         }
 
+#pragma unroll 1
+        for (int rr = 0; rr < ROWS; ++rr) {
+        if (ROWS > 1 && row + rr >= p.n_rows) break;  // odd tail: the pair's second row does not exist
+        const double2* ABr = AB + (ROWS > 1 ? rr * ICNV_ABS : 0);
+        const double* Cpr = Cp + (ROWS > 1 ? rr * ICNV_ABS : 0);
         // ======================= windows =======================
         double v[VPT];
         int nv[TPT];
@@ -303,7 +343,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                         double acc[LOUT];
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i) acc[i] = 0.0;
-                        const double2* P = AB + t.x;
+                        const double2* P = ABr + t.x;
 #pragma unroll
                         for (int q = 0; q < NQ_C + LOUT - 1; ++q) {
                             const double2 ab = P[q];
@@ -323,7 +363,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                         }
                         if constexpr (M3_C) {
 #pragma unroll
-                            for (int i = 0; i < LOUT; ++i) acc[i] += Cp[t.x + QSTAR_C + i];
+                            for (int i = 0; i < LOUT; ++i) acc[i] += Cpr[t.x + QSTAR_C + i];
                         }
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i)
@@ -333,13 +373,13 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                         for (int i = 0; i < LOUT; ++i) {
                             if (i < t.z) {
                                 double acc = 0.0;
-                                const double2* P = AB + t.x + i;
+                                const double2* P = ABr + t.x + i;
                                 for (int q = 0; q < NQ; ++q) {
                                     const double2 ab = P[q];
                                     acc = fma(w_alpha[q], ab.x, acc);
                                     acc = fma(w_beta[q], ab.y, acc);
                                 }
-                                if (qstar >= 0) acc += Cp[t.x + i + qstar];
+                                if (qstar >= 0) acc += Cpr[t.x + i + qstar];
                                 v[tt * LOUT + i] = acc * p.inv_sumw;
                             }
                         }
@@ -365,7 +405,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                     nv[tt] = 1;
                     double acc = 0.0;
                     if constexpr (GROUPED) {
-                        for (int g = 0; g < t.z; ++g) acc += AB[t.x + g].x;
+                        for (int g = 0; g < t.z; ++g) acc += ABr[t.x + g].x;
                     } else if constexpr (C64) {
                         for (int j = 0; j < t.z; ++j) acc += reinterpret_cast<const double*>(buf)[t.x + j];
                     } else {
@@ -397,7 +437,7 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                     f1 += __shfl_xor_sync(0xffffffffu, f1, sh);
                     f2 += __shfl_xor_sync(0xffffffffu, f2, sh);
                 }
-                double* orow = reinterpret_cast<double*>(p.out) + (size_t)row * p.ldo;
+                double* orow = reinterpret_cast<double*>(p.out) + (size_t)(row + rr) * p.ldo;
                 if (lane == 0)
                     reinterpret_cast<float2*>(orow + (size_t)((p.n_tasks + 31) >> 5) * (32 * LOUT))[ti >> 5] = make_float2(f1, f2);
                 double* o = orow + (size_t)(ti >> 5) * (32 * LOUT) + (ti & 31);
@@ -405,27 +445,30 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1) ? 2 : 1) smooth_ke
                 for (int i = 0; i < LOUT; ++i) o[i * 32] = v[tt * LOUT + i];
             }
         }
+        }  // rr
         ICNV_STAMP(4);
         __syncthreads();  // CTA-wide: tells the run-ahead warps that the partials have been read
         ICNV_STAMP(7);
         // the next row's barriers order the reuse of `sc`
     }
 #undef ICNV_STAMP
+#undef ICNV_ABS
+#undef ICNV_ROW_OFF
 }
 
 // ------------------------------------------------------------------------------------------------
 // instantiation table
-template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT>
+template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS = 1>
 static int launch_one(const SmoothParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT>;
+    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, NT, smem, stream>>>(p);
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }
-template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT>
+template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS = 1>
 static int occ_one(size_t smem, int* out) {
-    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT>;
+    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, NT, smem));
     return 0;
@@ -433,6 +476,10 @@ static int occ_one(size_t smem, int* out) {
 
 #define ICNV_DISPATCH(FN, ...)                                                                             \
     do {                                                                                                   \
+        if (tier == 0 && nwin == 100 && gs == 10 && tpt == 1 && rows == 2) {                               \
+            return bounded ? FN<0, 100, 10, true, false, 1, 2>(__VA_ARGS__) : FN<0, 100, 10, false, false, 1, 2>(__VA_ARGS__); \
+        }                                                                                                  \
+        if (rows != 1) break;                                                                              \
         if (tier == 0 && nwin == 100 && gs == 10 && tpt == 1) {                                            \
             return bounded ? FN<0, 100, 10, true, false, 1>(__VA_ARGS__) : FN<0, 100, 10, false, false, 1>(__VA_ARGS__); \
         }                                                                                                  \
@@ -455,13 +502,13 @@ static int occ_one(size_t smem, int* out) {
         }                                                                                                  \
     } while (0)
 
-int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, const SmoothParams& p, int grid,
+int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, const SmoothParams& p, int grid,
                   size_t smem, cudaStream_t stream) {
     ICNV_DISPATCH(launch_one, p, grid, smem, stream);
     set_error("smooth_launch: no kernel instantiation for this configuration");
     return -3;
 }
-int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, size_t smem, int* ctas_per_sm) {
+int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm) {
     ICNV_DISPATCH(occ_one, smem, ctas_per_sm);
     set_error("smooth_occupancy: no kernel instantiation for this configuration");
     return -3;

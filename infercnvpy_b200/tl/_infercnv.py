@@ -428,3 +428,15 @@ def infercnv(
             adata.layers[f"gene_values_{key_added}"] = per_gene
     else:
         return chr_pos, res, per_gene
+
+
+def _densify(csr_triple, n_genes, device):
+    """CSR block -> dense float32 block for the direct-form kernel (rare (window, step) pairs)."""
+    import torch
+
+    indptr, indices, data = csr_triple
+    n = indptr.numel() - 1
+    dense = torch.zeros((n, n_genes), dtype=torch.float32, device=device)
+    rows = torch.repeat_interleave(torch.arange(n, device=device), (indptr[1:] - indptr[:-1]))
+    dense[rows, indices.long()] = data
+    return dense

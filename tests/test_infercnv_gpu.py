@@ -358,6 +358,9 @@ def test_properties_at_scale():
         o1 = plan.center(plan.smooth(Xd[:5000], 3.0))[0]
         o2 = plan.center(plan.smooth(Xd[5000:], 3.0))[0]
         assert torch.equal(torch.cat([o1, o2]), pre)
+        # odd row counts (a CTA iteration may stage rows in pairs: the last pair is then half empty)
+        for n_odd in (1, 297, 2001):
+            assert torch.equal(plan.center(plan.smooth(Xd[7:7 + n_odd], 3.0))[0], pre[7:7 + n_odd])
         # (5) CSR input (densify on load) == dense input
         sub = Xd[:3000]
         csr = sub.to_sparse_csr()
