@@ -179,6 +179,10 @@ int icnv_louvain_sweep(const int64_t* indptr, const int32_t* indices, const floa
 int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* threads, int32_t* smem_bytes,
                           int32_t* n_sm);
 
+/* Average number of shared-memory wavefronts one warp-level gather of the smoothing kernel costs with this plan's
+ * gather schedule (1.0 = conflict-free; csrc/icnv_schedule.cu).  0 when the plan has no grouped layout. */
+int icnv_plan_gather_cost(const icnv_plan* plan, double* wavefronts_per_gather);
+
 /* Developer aid (tools/timeline.py): when dev_buf != NULL the smoothing kernel writes clock64 stamps
  * [grid][rows_per_cta][16] for the first rows_per_cta rows of every CTA.  NULL switches it off. */
 int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta);

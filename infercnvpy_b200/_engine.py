@@ -84,7 +84,12 @@ class DevicePlan:
     def launch_info(self) -> dict:
         v = [C.c_int32() for _ in range(4)]
         _lib.check(self.lib.icnv_plan_launch_info(self.handle, *[C.byref(x) for x in v]), "icnv_plan_launch_info")
-        return dict(ctas_per_sm=v[0].value, threads=v[1].value, smem_bytes=v[2].value, n_sm=v[3].value, tier=self.tier)
+        w = C.c_double()
+        _lib.check(self.lib.icnv_plan_gather_cost(self.handle, C.byref(w)), "icnv_plan_gather_cost")
+        return dict(
+            ctas_per_sm=v[0].value, threads=v[1].value, smem_bytes=v[2].value, n_sm=v[3].value, tier=self.tier,
+            wavefronts_per_gather=round(w.value, 4),
+        )
 
     def _stream(self):
         return _lib.stream_handle(self.device)

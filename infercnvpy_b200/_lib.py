@@ -38,6 +38,7 @@ SIGNATURES = {
     "icnv_apply_threshold": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_gene_values": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, C.c_int64, c_vp]),
     "icnv_plan_gene_coverage": (C.c_int, [c_vp, c_i32p]),
+    "icnv_plan_gather_cost": (C.c_int, [c_vp, C.POINTER(C.c_double)]),
     "icnv_plan_tmp_width": (C.c_int, [c_vp, c_i64p]),
     "icnv_dense_to_csr": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_rowabs_csr": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),

@@ -102,6 +102,10 @@ struct icnv_plan {
 
     DevBuf<double> flat_inv;
 
+    int rows = 1;                    // cell rows the grouped kernel stages per iteration (table layout depends on it)
+    bool permuted = false;           // gather tables carry the element position (bits 24..27 of off_w)
+    double gather_wavefronts = 0.0;  // shared-memory wavefronts per gather instruction of the schedule
+
     // ---- reference state
     bool have_ref = false, bounded = false, c64 = false;
 
@@ -182,7 +186,7 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
         const bool templ = (p.step == 10 && (p.window == 100 || p.window == 250));
         if (templ && p.n_tasks_g <= NT && smem_grouped(p, 0) <= SMEM_MAX) {
             *c = {0, p.window, p.gs, 1, smem_grouped(p, 0)};
-            if (p.window == 100 && smooth_rows_default() == 2 && smem_grouped(p, 0, 2) <= SMEM_MAX) {
+            if (p.rows == 2) {  // decided at plan creation (the gather tables are laid out for it)
                 c->rows = 2;
                 c->smem = smem_grouped(p, 0, 2);
             }
@@ -302,96 +306,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         p->NGpad = (p->NG + 3) / 4 * 4;
         if (p->NGpad == 0) p->NGpad = 4;
         p->Gpad = (n_genes + 1 + 3) / 4 * 4;
-        // ---- assign groups to (warp-block, u, lane) slots.
-        // A warp-level gather LDS for (wb, u, j) reads element j of the 32 groups in that slot set; its cost
-        // is the largest number of distinct addresses that fall into one shared-memory bank.  Genes are not
-        // position-sorted in memory, so with groups laid out in natural order that is ~3.5 wavefronts per
-        // LDS.  A constructive greedy (take, for every lane slot, the unassigned group that adds the fewest
-        // bank collisions over all j) brings it to ~2.0.  Lane l only takes groups with g % 8 == l % 8 so
-        // the 16-byte partial-sum stores AB[g] of a quarter-warp hit 8 different bank groups.
-        const int nquads = p->NGpad / 4;
-        const int n_wb = (nquads + 31) / 32;
-        const int nsets = n_wb * 4;
-        std::vector<int32_t> gcol((size_t)p->NG * gs, -1);  // column of element j of group g, -1 = pad
-        for (int c = 0; c < n_seg; ++c) {
-            const int32_t s0 = p->seg_off[c];
-            const int32_t Gc = p->seg_off[c + 1] - s0;
-            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g)
-                for (int j = 0; j < gs; ++j) {
-                    const int32_t pos = (g - gbase[c]) * gs + j;
-                    if (pos < Gc) gcol[(size_t)g * gs + j] = p->gene_idx[s0 + pos];
-                }
-        }
-        auto bank_of = [&](int32_t g, int j) {
-            const int32_t col = gcol[(size_t)g * gs + j];
-            return (col < 0 ? n_genes : col) & 31;
-        };
-        std::vector<int32_t> slot_group((size_t)nsets * 32, -1);
-        {
-            std::vector<std::vector<int32_t>> pool(8);
-            for (int32_t g = 0; g < p->NG; ++g) pool[g & 7].push_back(g);
-            std::vector<int> cnt((size_t)gs * 32), mx(gs);
-            for (int sidx = 0; sidx < nsets; ++sidx) {
-                std::fill(cnt.begin(), cnt.end(), 0);
-                std::fill(mx.begin(), mx.end(), 0);
-                for (int lane = 0; lane < 32; ++lane) {
-                    auto& cand = pool[lane & 7];
-                    if (cand.empty()) continue;
-                    long best_score = -1;
-                    size_t best_k = 0;
-                    for (size_t k = 0; k < cand.size(); ++k) {
-                        long add = 0, load = 0;
-                        for (int j = 0; j < gs; ++j) {
-                            const int nc = cnt[(size_t)j * 32 + bank_of(cand[k], j)] + 1;
-                            add += nc > mx[j] ? nc - mx[j] : 0;
-                            load += nc;
-                        }
-                        const long score = add * 4096 + load;
-                        if (best_score < 0 || score < best_score) {
-                            best_score = score;
-                            best_k = k;
-                        }
-                    }
-                    const int32_t g = cand[best_k];
-                    cand[best_k] = cand.back();
-                    cand.pop_back();
-                    slot_group[(size_t)sidx * 32 + lane] = g;
-                    for (int j = 0; j < gs; ++j) {
-                        int& c2 = cnt[(size_t)j * 32 + bank_of(g, j)];
-                        c2 += 1;
-                        if (c2 > mx[j]) mx[j] = c2;
-                    }
-                }
-            }
-            for (int c8 = 0; c8 < 8; ++c8)
-                if (!pool[c8].empty()) {
-                    set_error("internal: group slots exhausted");
-                    return ICNV_EINVAL;
-                }
-        }
-        // tables in kernel order: entry ((wb*gs + j)*32 + lane)*4 + u  <->  element j of the group in slot (wb, u, lane)
-        const size_t n_entries = (size_t)n_wb * gs * 32 * 4;
-        uint32_t raw_base = 0;
-        if (smooth_raw_base(&raw_base)) return ICNV_ECUDA;
-        p->raw_base = raw_base;
-        std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
-        std::vector<int32_t> cols(n_entries, -1);
-        std::vector<int32_t> grp((size_t)n_wb * 32 * 4, p->NGpad);  // empty slots store their zeros to a pad group
-        for (int wb = 0; wb < n_wb; ++wb)
-            for (int lane = 0; lane < 32; ++lane)
-                for (int u = 0; u < 4; ++u) {
-                    const int32_t g = slot_group[((size_t)wb * 4 + u) * 32 + lane];
-                    if (g < 0) continue;
-                    grp[((size_t)wb * 32 + lane) * 4 + u] = g;
-                    for (int j = 0; j < gs; ++j) {
-                        const int32_t col = gcol[(size_t)g * gs + j];
-                        if (col < 0) continue;
-                        const size_t e = (((size_t)wb * gs + j) * 32 + lane) * 4 + u;
-                        off[e] = raw_base + (uint32_t)col * 4u;
-                        cols[e] = col;
-                    }
-                }
-        // weights: within a group the pyramid is linear in j except (at most) the group holding the peak
+        // ---- weights: within a group the pyramid is linear in j except (at most) the group holding the peak
         std::vector<double> alpha(p->NQ, 0.0), beta(p->NQ, 0.0), cw(gs, 0.0);
         p->qstar = -1;
         for (int q = 0; q < p->NQ; ++q) {
@@ -424,6 +339,71 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             }
         }
         p->n_tasks_g = (int32_t)tasks.size();
+
+        // ---- assign groups to (warp-block, u, lane) slots and order every lane's walk over its group: icnv_schedule.cu.
+        // The permuted walk needs the element position j in the table entry (bits 24..27) and is what the templated
+        // kernel without a peak group decodes (tier 0, window 100); every other kernel walks j = 0..gs-1.
+        const int nquads = p->NGpad / 4;
+        const int n_wb = (nquads + 31) / 32;
+        const int nsets = n_wb * 4;
+        std::vector<int32_t> gcol((size_t)p->NG * gs, -1);  // column of element j of group g, -1 = pad
+        for (int c = 0; c < n_seg; ++c) {
+            const int32_t s0 = p->seg_off[c];
+            const int32_t Gc = p->seg_off[c + 1] - s0;
+            for (int32_t g = gbase[c]; g < gbase[c + 1]; ++g)
+                for (int j = 0; j < gs; ++j) {
+                    const int32_t pos = (g - gbase[c]) * gs + j;
+                    if (pos < Gc) gcol[(size_t)g * gs + j] = p->gene_idx[s0 + pos];
+                }
+        }
+        p->permuted = (s == 10 && n == 100) && p->qstar < 0 && gs <= 16 && p->n_tasks_g <= NT && smem_grouped(*p, 0) <= SMEM_MAX;
+        std::vector<int32_t> slot_group;
+        std::vector<uint8_t> order;
+        // ICNV_GATHER_PERM=0 (developer A/B): keep the natural walk; the entries still carry j
+        const char* perm_env = std::getenv("ICNV_GATHER_PERM");
+        const bool optimise_walk = p->permuted && !(perm_env && perm_env[0] == '0');
+        p->gather_wavefronts = schedule_gathers(gcol, p->NG, gs, n_genes, nsets, optimise_walk, slot_group, order);
+        if (p->gather_wavefronts < 0) {
+            set_error("internal: group slots exhausted");
+            return ICNV_EINVAL;
+        }
+        // tables in kernel order: entry ((unit*gs + t)*32 + lane)*2 + (u & 1), unit = 2*wb + u/2  <->  the element the lane in
+        // slot (wb, u, lane) reads at step t
+        const size_t n_entries = (size_t)n_wb * gs * 32 * 4;
+        // the kernel that will run decides the unit width: row pairs (templated window 100 that fits twice) walk whole
+        // warp-blocks, everything else half warp-blocks
+        const bool pairs = p->permuted && smooth_rows_default() == 2 && smem_grouped(*p, 0, 2) <= SMEM_MAX;
+        const int uw = ICNV_UNIT_WIDTH(pairs ? 2 : 1);
+        p->rows = pairs ? 2 : 1;
+        uint32_t raw_base = 0;
+        if (smooth_raw_base(&raw_base)) return ICNV_ECUDA;
+        p->raw_base = raw_base;
+        if (p->permuted && (raw_base + (uint32_t)p->Gpad * 4u * 2u) >= (1u << 24)) {
+            set_error("internal: shared window address does not fit the table entry");
+            return ICNV_EINVAL;
+        }
+        std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
+        std::vector<int32_t> cols(n_entries, -1);
+        std::vector<int32_t> grp((size_t)n_wb * 32 * 4, p->NGpad);  // empty slots store their zeros to a pad group
+        for (int wb = 0; wb < n_wb; ++wb)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int u = 0; u < 4; ++u) {
+                    const int32_t g = slot_group[((size_t)wb * 4 + u) * 32 + lane];
+                    if (g < 0) continue;
+                    // work unit = 32 lanes x uw groups (uw = 4: a whole warp-block, uw = 2: half of one)
+                    const size_t unit = (size_t)wb * (4 / uw) + (u / uw);
+                    grp[(unit * 32 + lane) * uw + (u % uw)] = g;
+                    for (int t = 0; t < gs; ++t) {
+                        const int j = order[(((size_t)wb * 4 + u) * 32 + lane) * gs + t];  // element read at step t
+                        const int32_t col = gcol[(size_t)g * gs + j];
+                        const size_t e = ((unit * gs + t) * 32 + lane) * uw + (u % uw);
+                        if (col >= 0) {
+                            off[e] = raw_base + (uint32_t)col * 4u;
+                            cols[e] = col;
+                        }
+                        if (p->permuted) off[e] |= (uint32_t)j << 24;  // pads carry their j too (x = 0 either way)
+                    }
+                }
         if (p->off_w.upload(off) || p->cols_w.upload(cols) || p->grp_w.upload(grp) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
             p->cw.upload(cw) || p->tasks_g.upload(tasks))
             return ICNV_ECUDA;
@@ -505,7 +485,7 @@ int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* thread
     rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
     if (rc) return rc;
     if (ctas_per_sm) *ctas_per_sm = occ;
-    if (threads) *threads = NT;
+    if (threads) *threads = smooth_threads(ch.rows);
     if (smem_bytes) *smem_bytes = (int32_t)ch.smem;
     if (n_sm) *n_sm = plan->n_sm;
     return ICNV_OK;
@@ -650,6 +630,12 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
     sp.dbg = g_dbg_ptr;
     sp.dbg_rows = g_dbg_rows;
     sp.use_tma = sp.X && (sp.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp.X) & 15) == 0) && (plan->G % 4 == 0);
+    {
+        const char* e = std::getenv("ICNV_L2_PREFETCH");  // developer A/B switch
+        sp.l2_prefetch = (e && e[0] == '0') ? 0 : 1;
+        const char* e2 = std::getenv("ICNV_SPLIT_ROWS");
+        sp.split_rows = (e2 && e2[0] == '0') ? 0 : 1;
+    }
     int occ = 0;
     rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
     if (rc) return rc;
@@ -762,6 +748,12 @@ int icnv_gene_values(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t
         gp.scratch = plan->gv_scratch.ptr;
     }
     return genevals_launch(gp, grid, smem < 16 ? 16 : smem, (cudaStream_t)stream);
+}
+
+int icnv_plan_gather_cost(const icnv_plan* plan, double* wavefronts_per_gather) {
+    if (!plan || !wavefronts_per_gather) return ICNV_EINVAL;
+    *wavefronts_per_gather = plan->group_ok ? plan->gather_wavefronts : 0.0;
+    return ICNV_OK;
 }
 
 int icnv_plan_gene_coverage(const icnv_plan* plan, int32_t* n_covered) {

@@ -10,6 +10,10 @@ namespace icnv {
 
 constexpr int NT = 512;         // threads per CTA of the smoothing kernel
 constexpr int NW = NT / 32;     // warps per CTA
+// threads per CTA of the smoothing kernel that stages `rows` cell rows per iteration
+__host__ __device__ constexpr int smooth_threads(int rows) { return NT + 0 * rows; }
+// groups per lane of one phase-2 work unit (table layout [unit][step][lane][u < width]) for a kernel staging `rows` rows
+#define ICNV_UNIT_WIDTH(rows) ((rows) == 2 ? 4 : 2)
 #ifndef ICNV_LOUT
 #define ICNV_LOUT 9
 #endif
@@ -41,16 +45,19 @@ struct SmoothParams {
     int32_t G;        // columns of X
     int32_t Gpad;     // staged floats (>= G+1, multiple of 4); slot G is the zero pad
     int32_t use_tma;  // row base and pitch 16-byte aligned -> cp.async.bulk
+    int32_t split_rows;   // row pairs: give every staged row its own group warps in phase 3
+    int32_t l2_prefetch;  // prefetch the next iteration's rows into L2 while this one is gathered
     // ---- grouped tiers (0/1)
     int32_t gs;       // genes per group (== step)
     int32_t NG;       // groups
     int32_t NGpad;    // multiple of 4
     int32_t NQ;       // groups per window
     int32_t qstar;    // group-in-window holding the pyramid peak (non-linear weights), -1 if none
-    // Per-gene tables in the order the kernel walks them: [warp-block of 32 quads][j < gs][lane][u < 4];
-    // entry (wb, j, lane, u) belongs to element j of group grp_w[(wb*32 + lane)*4 + u] (host-optimised
-    // assignment that minimises shared-memory bank collisions of the gathers).
-    const int32_t* grp_w;   // [warp-block][lane][u] group index (NGpad = unused slot)
+    // Per-gene tables in the order the kernel walks them: [work unit of 32 lanes x 2 groups][step t < gs][lane][u < 2];
+    // entry (unit, t, lane, u) belongs to the element of group grp_w[(unit*32 + lane)*2 + u] that the lane reads at
+    // step t (host-optimised assignment and walk order that minimise shared-memory bank collisions of the gathers,
+    // icnv_schedule.cu).  Two consecutive units form one warp-block of 32 quads (the slot sets 4*wb .. 4*wb+3).
+    const int32_t* grp_w;   // [unit][lane][u] group index (NGpad = unused slot)
     const uint32_t* off_w;  // shared-window BYTE address of the gene inside the staged raw row (zero pad slot = gene G)
     uint32_t raw_base;      // shared-window address of raw[0] baked into off_w (checked by the kernel)
     const float* lo_w;      // reference lower bound (== ref when one category)
@@ -140,6 +147,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// named barriers: `count` threads (a multiple of 32) take part; arrive does not block
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+// Ask the TMA engine to pull [src, src + bytes) into L2 (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
     float4 v;
     asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -148,6 +166,16 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
 __device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
     uint4 v;
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_nc_f2(const float* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_nc_u2(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
@@ -172,6 +200,9 @@ int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, i
                   size_t smem, cudaStream_t stream);
 int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm);
 
+// icnv_schedule.cu (host only)
+double schedule_gathers(const std::vector<int32_t>& gcol, int NG, int gs, int n_genes, int nsets, bool permute,
+                        std::vector<int32_t>& slot_group, std::vector<uint8_t>& order);
 int genevals_launch(const GeneValParams& p, int grid, size_t smem, cudaStream_t st);
 
 }  // namespace icnv

@@ -45,8 +45,9 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 // gather-table entry once for two rows — the tables (160 KB per sweep, L2 -> L1) are the largest removable share of the
 // kernel's l1tex work — at the price of one CTA per SM (2 x 80 KB of staged rows + 2 x 32 KB of partials).
 template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS>
-__global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 : 1) smooth_kernel(const SmoothParams p) {
+__global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 : 1) smooth_kernel(const SmoothParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NTH = smooth_threads(ROWS), NWH = NTH / 32;  // row pairs run 32 warps (64 registers each)
     Scratch* sc = reinterpret_cast<Scratch*>(smem);
     unsigned char* carve = smem + SCRATCH_BYTES;
 
@@ -54,15 +55,20 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
     // windows, median, write-out) are the HIGHEST physical warp ids, which the warp scheduler favours;
     // the run-ahead gather warps take the low ids.
     const int lane = threadIdx.x & 31;
-    const int warp = NW - 1 - (int)(threadIdx.x >> 5);
+    const int warp = NWH - 1 - (int)(threadIdx.x >> 5);
     const int tid = warp * 32 + lane;
-    constexpr int ISSUER = NT - 32;  // lane 0 of the last logical warp (a run-ahead warp) drives the TMA
+    constexpr int ISSUER = NTH - 32;  // lane 0 of the last logical warp (a run-ahead warp) drives the TMA
     constexpr bool GROUPED = TIER < 2;
     constexpr int NQ_C = (TIER == 0) ? NWIN / GS : 0;
     constexpr bool M3_C = (TIER == 0) && ((NWIN / 2) % GS != 0);
     constexpr int QSTAR_C = M3_C ? (NWIN / 2) / GS : -1;
     static_assert(TIER != 0 || NWIN % 2 == 0, "tier 0 instantiations use even windows");
     constexpr int VPT = TPT * LOUT;
+    // groups per lane in one phase-2 work unit.  Row pairs keep whole warp-blocks: a run-ahead warp can only gather ONE
+    // unit before it has to wait for the partial-sum buffer, so bigger units overlap more of phase 3.
+    constexpr int UW = ICNV_UNIT_WIDTH(ROWS);
+    // permuted walk (icnv_schedule.cu): step t of a lane reads element j = entry >> 24 of its group, not element t
+    constexpr bool PERM = (TIER == 0) && !M3_C;
     static_assert(ROWS == 1 || TIER < 2, "row pairs are a feature of the grouped tiers");
 #define ICNV_ABS (p.NGpad + PAD_GROUPS) /* partial-sum slots per staged row */
 
@@ -106,25 +112,25 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
     if constexpr (GROUPED) {
 #pragma unroll
         for (int rr = 0; rr < ROWS; ++rr) {
-            for (int i = p.G + tid; i < p.Gpad; i += NT) raw[rr * p.Gpad + i] = 0.f;
-            for (int i = p.NG + tid; i < ICNV_ABS; i += NT) {
+            for (int i = p.G + tid; i < p.Gpad; i += NTH) raw[rr * p.Gpad + i] = 0.f;
+            for (int i = p.NG + tid; i < ICNV_ABS; i += NTH) {
                 AB[(ROWS > 1 ? rr * ICNV_ABS : 0) + i] = make_double2(0.0, 0.0);
                 if (Cp) Cp[(ROWS > 1 ? rr * ICNV_ABS : 0) + i] = 0.0;
             }
         }
         if constexpr (TIER == 1) {
-            for (int i = tid; i < NQ; i += NT) {
+            for (int i = tid; i < NQ; i += NTH) {
                 w_alpha[i] = p.alpha[i];
                 w_beta[i] = p.beta[i];
             }
-            for (int i = tid; i < gs; i += NT) w_c[i] = p.cw[i];
+            for (int i = tid; i < gs; i += NTH) w_c[i] = p.cw[i];
         }
         if (tid == 0) {
             mbar_init(&sc->mbar, 1);
             mbar_fence_init();
         }
     } else {
-        for (int i = tid; i < p.window; i += NT) wdir[i] = p.wdir[i];
+        for (int i = tid; i < p.window; i += NTH) wdir[i] = p.wdir[i];
     }
     if (tid == 0) {
         sc->next_wb[0] = 0;
@@ -149,22 +155,46 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
         }
     };
 
+    // The staged rows are single-buffered (no room for a second set), so the fill of iteration i+1 cannot start before
+    // the gathers of iteration i are done.  HBM is kept streaming anyway by prefetching the rows of iteration i+1 into L2
+    // while iteration i is still being gathered; the later shared-memory fill is an L2 hit.
+    auto prefetch_row = [&](int64_t r) {
+        const int nvalid = (int)min((int64_t)ROWS, p.n_rows - r);
+        constexpr uint32_t CH = 16384;
+        for (int rr = 0; rr < nvalid; ++rr) {
+            const char* src = reinterpret_cast<const char*>(p.X + (r + rr) * p.ldx);
+            for (uint32_t off = 0; off < row_bytes; off += CH) bulk_prefetch_l2(src + off, min(CH, row_bytes - off));
+        }
+    };
+
     int64_t row = (int64_t)blockIdx.x * ROWS;  // first row of this iteration's group of ROWS
     const bool tma = GROUPED && dense && p.use_tma;
-    if (tma && tid == ISSUER && row < p.n_rows) issue_row(row);
+    if (tma && tid == ISSUER && row < p.n_rows) {
+        issue_row(row);
+        if (p.l2_prefetch && row + (int64_t)gridDim.x * ROWS < p.n_rows) prefetch_row(row + (int64_t)gridDim.x * ROWS);
+    }
 
     const float clipf = p.clipf;
     const int nquads = p.NGpad >> 2;
-    const int n_wb = (nquads + 31) >> 5;
-    // Only the warps that own output values ("group") take part in phase 3 / median / write-out; the others
-    // go straight to the next row and work ahead on its gathers (barrier 1 = group only, barrier 0 = CTA).
-    const int n_group = min(NT, ((p.n_tasks + 31) >> 5) << 5);
+    const int n_units = ((nquads + 31) >> 5) * (4 / UW);  // phase-2 work units handed out through next_wb
+    // Only the warps that own output values ("group") take part in phase 3 / write-out; the others go straight to
+    // the next iteration and work ahead on its gathers.  With row pairs and enough warps every staged row has its own
+    // set of group warps (split_rows), which halves the length of phase 3.
+    //   barrier 0 (CTA)      : gathers of this iteration done -> partials complete, staged rows dead
+    //   barrier 1 (CTA)      : group warps ARRIVE when they have read the partials of iteration i; the other warps SYNC
+    //                          on it before their first partial-sum store of iteration i+1
+    //   barrier 2 (group)    : the same hand-over among the group warps themselves
+    const int n_group1 = ((p.n_tasks + 31) >> 5) << 5;
+    const bool split_rows = ROWS > 1 && TPT == 1 && ROWS * n_group1 <= NTH && p.split_rows;
+    const int n_group = min(NTH, split_rows ? ROWS * n_group1 : n_group1);
     const bool in_group = tid < n_group;
+    const int my_rr = split_rows ? tid / n_group1 : 0;       // staged row whose outputs this thread computes
+    const int tix = split_rows ? tid - my_rr * n_group1 : tid;  // its first task
     // task descriptors are row-invariant: fetch them once
     int4 task[TPT];
 #pragma unroll
     for (int tt = 0; tt < TPT; ++tt) {
-        const int ti = tid + tt * NT;
+        const int ti = tix + tt * NTH;
         task[tt] = ti < p.n_tasks ? __ldg(reinterpret_cast<const int4*>(p.tasks) + ti) : make_int4(0, 0, 0, 0);
     }
     int it = 0;
@@ -186,17 +216,17 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
             } else if (dense) {
                 for (int rr = 0; rr < ROWS && row + rr < p.n_rows; ++rr) {
                     const float* src = p.X + (row + rr) * p.ldx;
-                    for (int i = tid; i < p.G; i += NT) raw[rr * p.Gpad + i] = __ldg(src + i);
+                    for (int i = tid; i < p.G; i += NTH) raw[rr * p.Gpad + i] = __ldg(src + i);
                 }
                 __syncthreads();
             } else {
                 // CSR: densify on load (the reference densifies too, _infercnv.py:423)
                 float4* r4 = reinterpret_cast<float4*>(raw);
-                for (int i = tid; i < ROWS * (p.Gpad >> 2); i += NT) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = tid; i < ROWS * (p.Gpad >> 2); i += NTH) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 __syncthreads();
                 for (int rr = 0; rr < ROWS && row + rr < p.n_rows; ++rr) {
                     const int64_t e0 = p.indptr[row + rr], e1 = p.indptr[row + rr + 1];
-                    for (int64_t e = e0 + tid; e < e1; e += NT) raw[rr * p.Gpad + __ldg(p.indices + e)] = __ldg(p.data + e);
+                    for (int64_t e = e0 + tid; e < e1; e += NTH) raw[rr * p.Gpad + __ldg(p.indices + e)] = __ldg(p.data + e);
                 }
                 __syncthreads();
             }
@@ -207,44 +237,67 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
             // warp-blocks of 32 quads are handed out dynamically: warps that are not in the group arrive
             // here early (they skipped the median of the previous row) and take most of them
             int* next_wb = &sc->next_wb[it & 1];
+            bool handed_over = in_group || it == 0;  // group warps synchronise on barrier 2 after their phase 3
             while (true) {
                 int wb = 0;
                 if (lane == 0) wb = atomicAdd(next_wb, 1);
                 wb = __shfl_sync(0xffffffffu, wb, 0);
-                if (wb >= n_wb) break;
-                const int quad = (wb << 5) + lane;  // slot index; every slot of every warp-block is valid
-                double a[ROWS][4], b[ROWS][4], c[ROWS][4];
+                if (wb >= n_units) break;
+                // `wb` is a work unit = half a warp-block: 32 lanes x UW = 2 groups (fine enough for the run-ahead warps
+                // to keep taking units while the group warps are in phase 3)
+                const int pairslot = (wb << 5) + lane;  // slot index; every slot of every unit is valid
+                double a[ROWS][UW], b[ROWS][UW], c[ROWS][UW];
 #pragma unroll
                 for (int rr = 0; rr < ROWS; ++rr)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) a[rr][u] = b[rr][u] = c[rr][u] = 0.0;
-                // table entry (wb, j, lane, u): ((wb*gs + j)*32 + lane)*4 + u
-                const size_t tbase = ((size_t)wb * gs * 32 + lane) * 4;
+                    for (int u = 0; u < UW; ++u) a[rr][u] = b[rr][u] = c[rr][u] = 0.0;
+                // table entry (unit, j, lane, u): ((unit*gs + j)*32 + lane)*UW + u
+                const size_t tbase = ((size_t)wb * gs * 32 + lane) * UW;
                 const uint32_t* ip = p.off_w + tbase;
                 const float* lp = p.lo_w + tbase;
                 const float* hp = p.hi_w + tbase;
                 auto body = [&](int j, double cwj) {
-                    const uint4 id = ldg_nc_u4(ip + j * 128);
-                    const float4 lo = ldg_nc_f4(lp + j * 128);
-                    float4 hi = lo;
-                    if constexpr (BOUNDED) hi = ldg_nc_f4(hp + j * 128);
                     // table entries are complete shared-window addresses (raw base baked in by the host); the second
                     // row of a pair sits row_off bytes further
-                    const float l4[4] = {lo.x, lo.y, lo.z, lo.w};
-                    const float h4[4] = {hi.x, hi.y, hi.z, hi.w};
-                    float x[ROWS][4];
+                    float l4[UW], h4[UW];
+                    uint32_t ad[UW];
+                    if constexpr (UW == 4) {
+                        const uint4 id = ldg_nc_u4(ip + j * (32 * UW));
+                        const float4 lo = ldg_nc_f4(lp + j * (32 * UW));
+                        float4 hi = lo;
+                        if constexpr (BOUNDED) hi = ldg_nc_f4(hp + j * (32 * UW));
+                        ad[0] = id.x, ad[1] = id.y, ad[2] = id.z, ad[3] = id.w;
+                        l4[0] = lo.x, l4[1] = lo.y, l4[2] = lo.z, l4[3] = lo.w;
+                        h4[0] = hi.x, h4[1] = hi.y, h4[2] = hi.z, h4[3] = hi.w;
+                    } else {
+                        const uint2 id = ldg_nc_u2(ip + j * (32 * UW));
+                        const float2 lo = ldg_nc_f2(lp + j * (32 * UW));
+                        float2 hi = lo;
+                        if constexpr (BOUNDED) hi = ldg_nc_f2(hp + j * (32 * UW));
+                        ad[0] = id.x, ad[1] = id.y;
+                        l4[0] = lo.x, l4[1] = lo.y;
+                        h4[0] = hi.x, h4[1] = hi.y;
+                    }
+                    float x[ROWS][UW];
+                    double jd[UW];
+                    if constexpr (PERM) {
+#pragma unroll
+                        for (int u = 0; u < UW; ++u) {
+                            // exact int -> double without I2F: 2^52 + j carries j in the low mantissa bits
+                            jd[u] = __hiloint2double(0x43300000, (int)(ad[u] >> 24)) - 4503599627370496.0;
+                            ad[u] &= 0x00FFFFFFu;
+                        }
+                    }
 #pragma unroll
                     for (int rr = 0; rr < ROWS; ++rr) {
                         const uint32_t ro = rr ? ICNV_ROW_OFF : 0u;
-                        x[rr][0] = lds_f32(id.x + ro);
-                        x[rr][1] = lds_f32(id.y + ro);
-                        x[rr][2] = lds_f32(id.z + ro);
-                        x[rr][3] = lds_f32(id.w + ro);
+#pragma unroll
+                        for (int u = 0; u < UW; ++u) x[rr][u] = lds_f32(ad[u] + ro);
                     }
 #pragma unroll
                     for (int rr = 0; rr < ROWS; ++rr)
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < UW; ++u) {
                             const float xv = x[rr][u];
                             float d;
                             if constexpr (BOUNDED)
@@ -254,7 +307,10 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
                             d = fminf(fmaxf(d, -clipf), clipf);
                             const double dd = (double)d;
                             a[rr][u] += dd;
-                            if (j > 0) b[rr][u] = fma((double)j, dd, b[rr][u]);
+                            if constexpr (PERM)
+                                b[rr][u] = fma(jd[u], dd, b[rr][u]);
+                            else if (j > 0)
+                                b[rr][u] = fma((double)j, dd, b[rr][u]);
                             if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
                         }
                 };
@@ -265,27 +321,42 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
                     for (int j = 0; j < gs; ++j) body(j, w_c[j]);
                 }
                 // lane l owns groups with g % 8 == l % 8: a quarter-warp's 16-byte stores hit 8 bank groups
-                const int4 gid = __ldg(reinterpret_cast<const int4*>(p.grp_w) + quad);
-                const int gq[4] = {gid.x, gid.y, gid.z, gid.w};
+                int gq[UW];
+                if constexpr (UW == 4) {
+                    const int4 gid = __ldg(reinterpret_cast<const int4*>(p.grp_w) + pairslot);
+                    gq[0] = gid.x, gq[1] = gid.y, gq[2] = gid.z, gq[3] = gid.w;
+                } else {
+                    const int2 gid = __ldg(reinterpret_cast<const int2*>(p.grp_w) + pairslot);
+                    gq[0] = gid.x, gq[1] = gid.y;
+                }
+                if (!handed_over) {
+                    named_bar_sync(1, NTH);  // the group has read the previous iteration's partials
+                    handed_over = true;
+                }
 #pragma unroll
                 for (int rr = 0; rr < ROWS; ++rr)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < UW; ++u) {
                         AB[(ROWS > 1 ? rr * ICNV_ABS : 0) + gq[u]] = make_double2(a[rr][u], b[rr][u]);
                         if (qstar >= 0) Cp[(ROWS > 1 ? rr * ICNV_ABS : 0) + gq[u]] = c[rr][u];
                     }
             }
+            if (!handed_over) named_bar_sync(1, NTH);  // took no warp-block this time: keep the barrier count whole
             ICNV_STAMP(2);
-                __syncthreads();  // gathers done: raw row is dead, partials visible
+            __syncthreads();  // gathers done: raw row is dead, partials visible
             ICNV_STAMP(3);
                 if (tid == ISSUER) {
                 *next_wb = 0;  // used again two rows from now
-                if (tma && row + (int64_t)gridDim.x * ROWS < p.n_rows) issue_row(row + (int64_t)gridDim.x * ROWS);
+                if (tma && row + (int64_t)gridDim.x * ROWS < p.n_rows) {
+                    issue_row(row + (int64_t)gridDim.x * ROWS);
+                    if (p.l2_prefetch && row + 2 * (int64_t)gridDim.x * ROWS < p.n_rows)
+                        prefetch_row(row + 2 * (int64_t)gridDim.x * ROWS);
+                }
             }
             ICNV_STAMP(13);
         } else {
             // direct tier: position-sorted centred row (float, or double for float64 centring)
-            for (int s = tid; s < p.n_sorted; s += NT) {
+            for (int s = tid; s < p.n_sorted; s += NTH) {
                 const float x = __ldg(p.X + row * p.ldx + p.idx_lin[s]);
                 if constexpr (C64) {
                     const double lo = reinterpret_cast<const double*>(p.lo_lin)[s];
@@ -317,13 +388,14 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
         }
 
         if (!in_group) {
-            __syncthreads();  // partials / sorted row consumed by the group: safe to start the next row
-                continue;
+            if constexpr (!GROUPED) __syncthreads();  // direct tier: the sorted row is reused right away
+            continue;  // grouped tiers: run ahead into the next iteration's gathers (hand-over on barrier 1)
         }
 
 #pragma unroll 1
-        for (int rr = 0; rr < ROWS; ++rr) {
-        if (ROWS > 1 && row + rr >= p.n_rows) break;  // odd tail: the pair's second row does not exist
+        for (int rr = my_rr; rr < ROWS; rr += (split_rows ? ROWS : 1)) {
+        const bool last_rr = split_rows || rr == ROWS - 1;
+        const bool row_exists = ROWS == 1 || row + rr < p.n_rows;  // odd tail: the pair's second row does not exist
         const double2* ABr = AB + (ROWS > 1 ? rr * ICNV_ABS : 0);
         const double* Cpr = Cp + (ROWS > 1 ? rr * ICNV_ABS : 0);
         // ======================= windows =======================
@@ -334,8 +406,8 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
             nv[tt] = 0;
 #pragma unroll
             for (int i = 0; i < LOUT; ++i) v[tt * LOUT + i] = INFINITY;
-            const int ti = tid + tt * NT;
-            if (ti < p.n_tasks) {
+            const int ti = tix + tt * NTH;
+            if (ti < p.n_tasks && row_exists) {
                 const int4 t = task[tt];
                 if ((t.w & 0xFF) == 0) {
                     nv[tt] = t.z;
@@ -417,11 +489,18 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
         }
 
         ICNV_STAMP(15);
+        if constexpr (GROUPED) {
+            if (last_rr) {  // all partials this thread needs are in registers: hand the buffer over
+                named_bar_arrive(1, NTH);
+                named_bar_sync(2, n_group);
+            }
+        }
+        if (!row_exists) continue;
         // ======================= write the smoothed row (tile order, fp64) =======================
 #pragma unroll
         for (int tt = 0; tt < TPT; ++tt) {
             // the 32 lanes of a warp write 32 consecutive values per instruction (256-byte lines)
-            const int ti = tid + tt * NT;
+            const int ti = tix + tt * NTH;
             if (ti < ((p.n_tasks + 31) & ~31)) {
                 // tile moments behind the values: they steer the median bracket of center_rows (fp32 is plenty)
                 double s1 = 0.0, s2 = 0.0;
@@ -447,9 +526,8 @@ __global__ void __launch_bounds__(NT, (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 :
         }
         }  // rr
         ICNV_STAMP(4);
-        __syncthreads();  // CTA-wide: tells the run-ahead warps that the partials have been read
+        if constexpr (!GROUPED) __syncthreads();  // direct tier: the sorted row has been read
         ICNV_STAMP(7);
-        // the next row's barriers order the reuse of `sc`
     }
 #undef ICNV_STAMP
 #undef ICNV_ABS
@@ -462,7 +540,7 @@ template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS 
 static int launch_one(const SmoothParams& p, int grid, size_t smem, cudaStream_t stream) {
     auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, NT, smem, stream>>>(p);
+    k<<<grid, smooth_threads(ROWS), smem, stream>>>(p);
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }
@@ -470,7 +548,7 @@ template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS 
 static int occ_one(size_t smem, int* out) {
     auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, NT, smem));
+    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, smooth_threads(ROWS), smem));
     return 0;
 }
 

@@ -23,12 +23,13 @@ with DevicePlan(layout, dev) as plan:
     plan.smooth(Xd, 3.0); torch.cuda.synchronize()
     lib.icnv_debug_set_timeline(None, 0)
 t = buf.cpu().numpy().astype(np.float64)
-rows = slice(4, min(R, N // grid - 2))   # steady state
+ROWS = 2 if (info['ctas_per_sm'] == 1 and info['tier'] == 0 and window == 100) else 1
+rows = slice(4, min(R, N // (grid * ROWS) - 2))   # steady state (iterations; an iteration stages ROWS rows)
 T = t[:, rows, :]
 def d(a, b): x = (T[..., b] - T[..., a]).ravel(); x = x[(T[..., a].ravel() > 0) & (T[..., b].ravel() > 0)]; return float(np.median(x)), float(np.mean(x))
-names = {(0,1): "wait row (mbarrier)", (1,2): "own phase-2 blocks", (2,3): "wait BAR_A", (3,13): "after BAR_A", (13,15): "phase 3 FMA loops",
-         (15,4): "tile-order stores", (4,7): "BAR_B", (0,7): "whole row"}
+names = {(0,1): "wait row (mbarrier)", (1,2): "own phase-2 blocks", (2,3): "wait BAR_A", (3,13): "after BAR_A", (13,15): "phase 3 reads+FMA (last row)", (15,4): "hand-over + stores (last row)", (13,4): "phase 3 + stores (all staged rows)",
+         (4,7): "BAR_B", (0,7): "whole iteration"}
 period = np.diff(t[:, 4:rows.stop, 0], axis=1).ravel()
-print(json.dumps(dict(N=N, window=window, grid=grid, period_median=float(np.median(period)), period_mean=float(period.mean()))))
+print(json.dumps(dict(N=N, window=window, grid=grid, rows_per_iteration=ROWS, period_median=float(np.median(period)), period_mean=float(period.mean()))))
 for k, v in names.items():
     m, a = d(*k); print(f"{v:32s} median {m:9.0f}  mean {a:9.0f} cycles")
