@@ -101,6 +101,11 @@ struct icnv_plan {
     DevBuf<Task> tasks_d;
 
     DevBuf<double> flat_inv;
+    std::vector<Task> tasks_d_host;
+    // parts of the direct kernel (runs of whole task tiles whose genes fit in shared memory), per staging dtype
+    DevBuf<int32_t> parts[2];
+    int32_t n_parts[2] = {0, 0};
+    size_t parts_smem[2] = {0, 0};
 
     int rows = 1;                    // cell rows the grouped kernel stages per iteration (table layout depends on it)
     bool permuted = false;           // gather tables carry the element position (bits 24..27 of off_w)
@@ -133,6 +138,8 @@ struct icnv_plan {
         wdir.release();
         tasks_d.release();
         flat_inv.release();
+        parts[0].release();
+        parts[1].release();
         colsum_partial.release();
         gv_first.release();
         gv_cnt.release();
@@ -197,17 +204,52 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
             return 0;
         }
     }
-    if (smem_direct(p, c64) > SMEM_MAX) {
-        set_error("gene axis too long for the shared-memory resident row of the direct kernel (" +
-                  std::to_string(p.n_sorted) + " genes" + (c64 ? ", float64 centring)" : ")"));
-        return ICNV_EUNSUPPORTED;
+    // direct form: any gene axis / window / step (the row is staged in parts, icnv_direct.cu)
+    *c = {2, 0, 0, 1, std::min(smem_direct(p, c64), SMEM_MAX - 1024), 1};
+    return 0;
+}
+
+// Parts of the direct kernel for one staging dtype: greedy runs of whole task tiles whose position-sorted genes fit
+// into `cap` staged elements.  Tasks are position-ordered, so a run's genes are one contiguous range.
+int build_parts(icnv_plan& p, bool c64) {
+    const int k = c64 ? 1 : 0;
+    if (p.n_parts[k] > 0 || p.n_tasks_d == 0) return 0;
+    const size_t elem = c64 ? 8 : 4;
+    const size_t avail = SMEM_MAX - 1024 - (size_t)p.window * 8;
+    const int64_t cap = (int64_t)(avail / elem) - 4;
+    const int n_tiles = (p.n_tasks_d + 31) / 32;
+    auto task_end = [&](const Task& t) -> int64_t {
+        return (t.w & 0xFF) ? (int64_t)t.x + t.z : (int64_t)t.x + (int64_t)(t.z - 1) * p.step + p.window;
+    };
+    std::vector<int32_t> parts;
+    int64_t max_len = 0;
+    int tile = 0;
+    while (tile < n_tiles) {
+        const int64_t s0 = p.tasks_d_host[(size_t)tile * 32].x;
+        int64_t s1 = s0;
+        int t1 = tile;
+        while (t1 < n_tiles) {
+            int64_t e = s1;
+            for (int ti = t1 * 32; ti < std::min(p.n_tasks_d, (t1 + 1) * 32); ++ti) e = std::max(e, task_end(p.tasks_d_host[ti]));
+            if (e - s0 > cap) break;
+            s1 = e;
+            ++t1;
+        }
+        if (t1 == tile) {
+            set_error("direct kernel: the genes of one tile of 32 tasks do not fit in shared memory (window " +
+                      std::to_string(p.window) + ", step " + std::to_string(p.step) + ")");
+            return ICNV_EUNSUPPORTED;
+        }
+        parts.push_back((int32_t)s0);
+        parts.push_back((int32_t)s1);
+        parts.push_back(tile);
+        parts.push_back(t1);
+        max_len = std::max(max_len, s1 - s0);
+        tile = t1;
     }
-    if (p.n_tasks_d > 4 * NT) {
-        set_error("output too wide for the register-resident median: K = " + std::to_string(p.K) + " > " +
-                  std::to_string(4 * NT * LOUT));
-        return ICNV_EUNSUPPORTED;
-    }
-    *c = {2, 0, 0, p.n_tasks_d <= NT ? 1 : 4, smem_direct(p, c64), 1};
+    p.n_parts[k] = (int32_t)(parts.size() / 4);
+    p.parts_smem[k] = ((size_t)p.window * 8 + (size_t)(max_len + 4) * elem + 15) / 16 * 16;
+    if (p.parts[k].upload(parts)) return ICNV_ECUDA;
     return 0;
 }
 
@@ -285,6 +327,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             }
         }
         p->n_tasks_d = (int32_t)tasks.size();
+        p->tasks_d_host = tasks;
         std::vector<double> w(n);
         for (int j = 0; j < n; ++j) w[j] = (double)pyr(n, j);
         if (p->idx_lin.upload(p->gene_idx) || p->tasks_d.upload(tasks) || p->wdir.upload(w)) return ICNV_ECUDA;
@@ -481,9 +524,11 @@ int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* thread
     Choice ch;
     int rc = choose(*plan, plan->c64, &ch);
     if (rc) return rc;
-    int occ = 0;
-    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
-    if (rc) return rc;
+    int occ = 1;
+    if (ch.tier < 2) {
+        rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
+        if (rc) return rc;
+    }
     if (ctas_per_sm) *ctas_per_sm = occ;
     if (threads) *threads = smooth_threads(ch.rows);
     if (smem_bytes) *smem_bytes = (int32_t)ch.smem;
@@ -596,6 +641,34 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
         set_error("smooth: CSR input is only fused into the grouped kernels; densify first for this (window, step)");
         return ICNV_EUNSUPPORTED;
     }
+    if (ch.tier == 2) {
+        const int k = plan->c64 ? 1 : 0;
+        rc = build_parts(*plan, plan->c64);
+        if (rc) return rc;
+        DirectParams dp;
+        memset(&dp, 0, sizeof(dp));
+        dp.X = sp.X;
+        dp.ldx = sp.ldx;
+        dp.n_rows = sp.n_rows;
+        dp.idx_lin = plan->idx_lin.ptr;
+        dp.lo_lin = plan->lo_lin.ptr;
+        dp.hi_lin = plan->hi_lin.ptr;
+        dp.wdir = plan->wdir.ptr;
+        dp.window = plan->window;
+        dp.step = plan->step;
+        dp.tasks = plan->tasks_d.ptr;
+        dp.n_tasks = plan->n_tasks_d;
+        dp.parts = reinterpret_cast<const int4*>(plan->parts[k].ptr);
+        dp.n_parts = plan->n_parts[k];
+        dp.clip = plan->c64 ? lfc_clip : (double)(float)lfc_clip;
+        dp.clipf = (float)lfc_clip;
+        dp.inv_sumw = plan->inv_sumw;
+        dp.flat_inv = plan->flat_inv.ptr;
+        dp.out = out;
+        dp.ldo = ldo;
+        const int grid = (int)std::min<int64_t>(sp.n_rows, (int64_t)plan->n_sm);
+        return direct_launch(dp, plan->bounded, plan->c64, grid, plan->parts_smem[k], (cudaStream_t)stream);
+    }
     sp.G = plan->G;
     sp.Gpad = plan->Gpad;
     sp.gs = plan->gs;
@@ -692,6 +765,9 @@ int icnv_center_rows(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t
         set_error("icnv_center_rows: intermediate pitch smaller than icnv_plan_tmp_width");
         return ICNV_EINVAL;
     }
+    if ((n_tasks + 31) / 32 > 28)  // wider than the warp-per-row kernel's byte counters: CTA-per-row selection
+        return center_wide_launch(tmp, n_rows, ld_tmp, plan->gv_kaddr.ptr, (int)plan->K, out, out_is_f64 != 0, ldo, row_stats,
+                                  plan->n_sm, (cudaStream_t)stream);
     return aux_center_rows(tmp, n_rows, ld_tmp, tasks, n_tasks, (int)plan->K, out, out_is_f64 != 0, ldo, row_stats, (cudaStream_t)stream);
 }
 

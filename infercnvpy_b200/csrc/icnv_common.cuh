@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace icnv {
@@ -89,6 +90,27 @@ struct SmoothParams {
     // optional developer timeline: [grid][dbg_rows][16] clock64 stamps (nullptr = off)
     long long* dbg;
     int32_t dbg_rows;
+};
+
+// general direct-form smoothing (icnv_direct.cu)
+struct DirectParams {
+    const float* X;
+    int64_t ldx, n_rows;
+    const int32_t* idx_lin;  // [n_sorted] matrix column of the s-th position-sorted gene
+    const void* lo_lin;      // [n_sorted] float or double (C64) lower bound (== reference when one category)
+    const void* hi_lin;
+    const double* wdir;      // [window] pyramid weights
+    int32_t window, step;
+    const Task* tasks;       // direct layout: x = first sorted gene
+    int32_t n_tasks;
+    const int4* parts;       // (first sorted gene, end, first tile, end tile): what is staged together
+    int32_t n_parts;
+    double clip;
+    float clipf;
+    double inv_sumw;
+    const double* flat_inv;
+    double* out;             // [n_rows, ldo] fp64, warp-tile order + tile moments (same as SmoothParams::out)
+    int64_t ldo;
 };
 
 // per-gene layer (icnv_genevals.cu)
@@ -200,6 +222,9 @@ int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, i
                   size_t smem, cudaStream_t stream);
 int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm);
 
+int direct_launch(const DirectParams& p, bool bounded, bool c64, int grid, size_t smem, cudaStream_t st);
+int center_wide_launch(const double* tmp, int64_t n_rows, int64_t ld, const int32_t* kaddr, int K, void* out, bool f64, int64_t ldo,
+                       double* row_stats, int n_sm, cudaStream_t st);
 // icnv_schedule.cu (host only)
 double schedule_gathers(const std::vector<int32_t>& gcol, int NG, int gs, int n_genes, int nsets, bool permute,
                         std::vector<int32_t>& slot_group, std::vector<uint8_t>& order);

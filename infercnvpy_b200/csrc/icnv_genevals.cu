@@ -12,20 +12,12 @@
 // so every store is coalesced (streaming, fp64) — the layer is a dense [n_rows, n_genes] float64 matrix (160 KB per cell
 // at 20k genes), which is what bounds this kernel: 8 * n_genes bytes written per cell.
 #include "icnv_common.cuh"
+#include "icnv_select.cuh"
 
 namespace icnv {
 
 constexpr int GV_NT = 512;
 
-
-__device__ __forceinline__ unsigned long long gv_ordered(double v) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double gv_unordered(unsigned long long k) {
-    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
-    return __longlong_as_double((long long)b);
-}
 
 // numpy's add.reduce over a contiguous float64 vector (pairwise summation, blocks of 128, 8 accumulators), which is what
 // np.mean of the per-gene list runs (:287): identical operation order => identical bits.
@@ -88,9 +80,7 @@ __device__ double np_pairwise_sum(F get, int a0, int n) {
 
 __global__ void __launch_bounds__(GV_NT, 1) gene_values_kernel(const GeneValParams p) {
     extern __shared__ __align__(16) unsigned char gv_smem[];
-    __shared__ int hist[256];
-    __shared__ unsigned long long sel_prefix, sel_min_gt;
-    __shared__ int sel_rank, sel_cnt_le;
+    __shared__ SelectSmem sel;
 
     double* sk = p.k_in_smem ? reinterpret_cast<double*>(gv_smem) : nullptr;
     double* sv = p.v_in_smem ? reinterpret_cast<double*>(gv_smem) + (p.k_in_smem ? p.K : 0)
@@ -115,88 +105,10 @@ __global__ void __launch_bounds__(GV_NT, 1) gene_values_kernel(const GeneValPara
             }
             sv[i] = s / (double)c;
         }
-        if (tid == 0) {
-            sel_prefix = 0ull;
-            sel_rank = (n - 1) >> 1;
-        }
         __syncthreads();  // (global scratch: writes by this CTA are visible to it after the barrier)
 
-        // ---- exact selection of rank (n-1)/2: most significant byte first
-        double m = 0.0;
-        if (n > 0) {
-            for (int pass = 0; pass < 8; ++pass) {
-                const int shift = 56 - 8 * pass;
-                if (tid < 256) hist[tid] = 0;
-                __syncthreads();
-                const unsigned long long prefix = sel_prefix;
-                for (int i = tid; i < n; i += GV_NT) {
-                    const unsigned long long key = gv_ordered(sv[i]);
-                    if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1);
-                }
-                __syncthreads();
-                if (tid < 32) {
-                    int c[8], tot = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        c[j] = hist[lane * 8 + j];
-                        tot += c[j];
-                    }
-                    int incl = tot;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const int rank = sel_rank;
-                    __syncwarp();
-                    const unsigned mm = __ballot_sync(0xffffffffu, incl > rank);
-                    const int owner = __ffs(mm) - 1;  // always found: the candidate set holds the rank
-                    if (lane == owner) {
-                        int below = incl - tot;
-                        int b = 0;
-                        for (; b < 7; ++b) {
-                            if (below + c[b] > rank) break;
-                            below += c[b];
-                        }
-                        sel_prefix = prefix | ((unsigned long long)(lane * 8 + b) << shift);
-                        sel_rank = rank - below;
-                    }
-                }
-                __syncthreads();
-            }
-            const unsigned long long k1 = sel_prefix;
-            double v1 = gv_unordered(k1), v2 = v1;
-            if ((n & 1) == 0) {
-                // second middle value: v1 again if enough copies of it, else the smallest value above
-                if (tid == 0) {
-                    sel_cnt_le = 0;
-                    sel_min_gt = ~0ull;
-                }
-                __syncthreads();
-                int le = 0;
-                unsigned long long mg = ~0ull;
-                for (int i = tid; i < n; i += GV_NT) {
-                    const unsigned long long key = gv_ordered(sv[i]);
-                    if (key <= k1)
-                        ++le;
-                    else if (key < mg)
-                        mg = key;
-                }
-                le = __reduce_add_sync(0xffffffffu, le);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long t = __shfl_xor_sync(0xffffffffu, mg, o);
-                    mg = t < mg ? t : mg;
-                }
-                if (lane == 0) {
-                    atomicAdd(&sel_cnt_le, le);
-                    atomicMin(&sel_min_gt, mg);
-                }
-                __syncthreads();
-                if ((n >> 1) >= sel_cnt_le) v2 = gv_unordered(sel_min_gt);
-            }
-            m = (v1 + v2) / 2.0;  // np.median: mean of the two middle values (:444)
-        }
+        // ---- exact np.median of the covered genes (:444)
+        const double m = cta_median<GV_NT>([&](int i) { return sv[i]; }, n, sel);
 
         // ---- centre, filter, natural-order write
         const double t = p.thr ? p.thr[row / p.chunk_rows] : -1.0;

@@ -20,8 +20,8 @@
 //            outputs skip phase 3 and run ahead into the next row's gathers.
 //   phase 3: one thread per LOUT=9 consecutive outputs slides over the partials (fp64 FMAs, weights
 //            are compile-time immediates in tier 0) and writes them in warp-tile order (256-byte lines).
-// Tier 2 ("direct") evaluates the reference formula literally from a position-sorted centred row in
-// smem; it covers every (window, step) and float64 centring and is the slow general fallback.
+// Tier 2 ("direct": every other (window, step), float64 centring, gene axes longer than shared memory) is
+// icnv_direct.cu.
 #include "icnv_common.cuh"
 
 namespace icnv {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
     const int warp = NWH - 1 - (int)(threadIdx.x >> 5);
     const int tid = warp * 32 + lane;
     constexpr int ISSUER = NTH - 32;  // lane 0 of the last logical warp (a run-ahead warp) drives the TMA
-    constexpr bool GROUPED = TIER < 2;
+    static_assert(TIER < 2 && !C64, "the direct form (tier 2, float64 centring) lives in icnv_direct.cu");
     constexpr int NQ_C = (TIER == 0) ? NWIN / GS : 0;
     constexpr bool M3_C = (TIER == 0) && ((NWIN / 2) % GS != 0);
     constexpr int QSTAR_C = M3_C ? (NWIN / 2) / GS : -1;
@@ -69,7 +69,6 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
     constexpr int UW = ICNV_UNIT_WIDTH(ROWS);
     // permuted walk (icnv_schedule.cu): step t of a lane reads element j = entry >> 24 of its group, not element t
     constexpr bool PERM = (TIER == 0) && !M3_C;
-    static_assert(ROWS == 1 || TIER < 2, "row pairs are a feature of the grouped tiers");
 #define ICNV_ABS (p.NGpad + PAD_GROUPS) /* partial-sum slots per staged row */
 
     // ---- carve shared memory
@@ -79,12 +78,10 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
     double* w_alpha = nullptr;
     double* w_beta = nullptr;
     double* w_c = nullptr;
-    void* buf = nullptr;
-    double* wdir = nullptr;
     const int gs = (TIER == 0) ? GS : p.gs;
     const int NQ = (TIER == 0) ? NQ_C : p.NQ;
     const int qstar = (TIER == 0) ? QSTAR_C : p.qstar;
-    if constexpr (GROUPED) {
+    {
         raw = reinterpret_cast<float*>(carve);
         carve += (size_t)ROWS * p.Gpad * 4;
         AB = reinterpret_cast<double2*>(carve);
@@ -101,15 +98,11 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
             w_c = reinterpret_cast<double*>(carve);
             carve += (size_t)gs * 8;
         }
-    } else {
-        wdir = reinterpret_cast<double*>(carve);
-        carve += (size_t)p.window * 8;
-        buf = carve;
     }
 
     // ---- one-time setup
     const bool dense = p.X != nullptr;
-    if constexpr (GROUPED) {
+    {
 #pragma unroll
         for (int rr = 0; rr < ROWS; ++rr) {
             for (int i = p.G + tid; i < p.Gpad; i += NTH) raw[rr * p.Gpad + i] = 0.f;
@@ -129,13 +122,11 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
             mbar_init(&sc->mbar, 1);
             mbar_fence_init();
         }
-    } else {
-        for (int i = tid; i < p.window; i += NTH) wdir[i] = p.wdir[i];
     }
     if (tid == 0) {
         sc->next_wb[0] = 0;
         sc->next_wb[1] = 0;
-        if (GROUPED && (smem_u32(raw) & 0xFFFFFFu) != p.raw_base) __trap();  // host baked a different base
+        if ((smem_u32(raw) & 0xFFFFFFu) != p.raw_base) __trap();  // host baked a different base
     }
     __syncthreads();
 
@@ -168,7 +159,7 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
     };
 
     int64_t row = (int64_t)blockIdx.x * ROWS;  // first row of this iteration's group of ROWS
-    const bool tma = GROUPED && dense && p.use_tma;
+    const bool tma = dense && p.use_tma;
     if (tma && tid == ISSUER && row < p.n_rows) {
         issue_row(row);
         if (p.l2_prefetch && row + (int64_t)gridDim.x * ROWS < p.n_rows) prefetch_row(row + (int64_t)gridDim.x * ROWS);
@@ -208,7 +199,7 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
     for (; row < p.n_rows; row += (int64_t)gridDim.x * ROWS, ++it) {
         ICNV_STAMP(0);
         // ======================= stage the raw row =======================
-        if constexpr (GROUPED) {
+        {
             if (tma) {
                 mbar_wait(&sc->mbar, parity);
                 parity ^= 1u;
@@ -233,9 +224,9 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
         }
 
         // ======================= centre + clip + partial sums =======================
-        if constexpr (GROUPED) {
-            // warp-blocks of 32 quads are handed out dynamically: warps that are not in the group arrive
-            // here early (they skipped the median of the previous row) and take most of them
+        {
+            // work units are handed out dynamically: warps that are not in the group arrive here early (they skipped
+            // phase 3 of the previous iteration) and take most of them
             int* next_wb = &sc->next_wb[it & 1];
             bool handed_over = in_group || it == 0;  // group warps synchronise on barrier 2 after their phase 3
             while (true) {
@@ -243,8 +234,7 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                 if (lane == 0) wb = atomicAdd(next_wb, 1);
                 wb = __shfl_sync(0xffffffffu, wb, 0);
                 if (wb >= n_units) break;
-                // `wb` is a work unit = half a warp-block: 32 lanes x UW = 2 groups (fine enough for the run-ahead warps
-                // to keep taking units while the group warps are in phase 3)
+                // `wb` is a work unit: 32 lanes x UW groups (a whole warp-block of quads for row pairs, half of one else)
                 const int pairslot = (wb << 5) + lane;  // slot index; every slot of every unit is valid
                 double a[ROWS][UW], b[ROWS][UW], c[ROWS][UW];
 #pragma unroll
@@ -354,42 +344,10 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                 }
             }
             ICNV_STAMP(13);
-        } else {
-            // direct tier: position-sorted centred row (float, or double for float64 centring)
-            for (int s = tid; s < p.n_sorted; s += NTH) {
-                const float x = __ldg(p.X + row * p.ldx + p.idx_lin[s]);
-                if constexpr (C64) {
-                    const double lo = reinterpret_cast<const double*>(p.lo_lin)[s];
-                    double d;
-                    if constexpr (BOUNDED) {
-                        const double hi = reinterpret_cast<const double*>(p.hi_lin)[s];
-                        // bounded result is written into an array of the matrix dtype (:428): round to fp32
-                        d = (double)x > hi ? (double)(float)((double)x - hi)
-                                           : ((double)x < lo ? (double)(float)((double)x - lo) : 0.0);
-                        d = (double)fminf(fmaxf((float)d, -clipf), clipf);
-                    } else {
-                        d = (double)x - lo;
-                        d = fmin(fmax(d, -p.clip), p.clip);
-                    }
-                    reinterpret_cast<double*>(buf)[s] = d;
-                } else {
-                    const float lo = reinterpret_cast<const float*>(p.lo_lin)[s];
-                    float d;
-                    if constexpr (BOUNDED) {
-                        const float hi = reinterpret_cast<const float*>(p.hi_lin)[s];
-                        d = x > hi ? x - hi : (x < lo ? x - lo : 0.f);
-                    } else {
-                        d = x - lo;
-                    }
-                    reinterpret_cast<float*>(buf)[s] = fminf(fmaxf(d, -clipf), clipf);
-                }
-            }
-            __syncthreads();
         }
 
         if (!in_group) {
-            if constexpr (!GROUPED) __syncthreads();  // direct tier: the sorted row is reused right away
-            continue;  // grouped tiers: run ahead into the next iteration's gathers (hand-over on barrier 1)
+            continue;  // run ahead into the next iteration's gathers (hand-over on barrier 1)
         }
 
 #pragma unroll 1
@@ -455,41 +413,19 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                                 v[tt * LOUT + i] = acc * p.inv_sumw;
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < LOUT; ++i) {
-                            if (i < t.z) {
-                                double acc = 0.0;
-                                const int s0 = t.x + i * p.step;
-                                if constexpr (C64) {
-                                    const double* B = reinterpret_cast<const double*>(buf) + s0;
-                                    for (int j = 0; j < p.window; ++j) acc = fma(wdir[j], B[j], acc);
-                                } else {
-                                    const float* B = reinterpret_cast<const float*>(buf) + s0;
-                                    for (int j = 0; j < p.window; ++j) acc = fma(wdir[j], (double)B[j], acc);
-                                }
-                                v[tt * LOUT + i] = acc * p.inv_sumw;
-                            }
-                        }
                     }
                 } else {
                     // chromosome not longer than the window: one flat mean (_infercnv.py:227-236)
                     nv[tt] = 1;
                     double acc = 0.0;
-                    if constexpr (GROUPED) {
-                        for (int g = 0; g < t.z; ++g) acc += ABr[t.x + g].x;
-                    } else if constexpr (C64) {
-                        for (int j = 0; j < t.z; ++j) acc += reinterpret_cast<const double*>(buf)[t.x + j];
-                    } else {
-                        for (int j = 0; j < t.z; ++j) acc += (double)reinterpret_cast<const float*>(buf)[t.x + j];
-                    }
+                    for (int g = 0; g < t.z; ++g) acc += ABr[t.x + g].x;
                     v[tt * LOUT] = acc * p.flat_inv[t.w >> 8];
                 }
             }
         }
 
         ICNV_STAMP(15);
-        if constexpr (GROUPED) {
+        {
             if (last_rr) {  // all partials this thread needs are in registers: hand the buffer over
                 named_bar_arrive(1, NTH);
                 named_bar_sync(2, n_group);
@@ -526,7 +462,6 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
         }
         }  // rr
         ICNV_STAMP(4);
-        if constexpr (!GROUPED) __syncthreads();  // direct tier: the sorted row has been read
         ICNV_STAMP(7);
     }
 #undef ICNV_STAMP
@@ -569,14 +504,6 @@ static int occ_one(size_t smem, int* out) {
         }                                                                                                  \
         if (tier == 1 && tpt == 4) {                                                                       \
             return bounded ? FN<1, 0, 0, true, false, 4>(__VA_ARGS__) : FN<1, 0, 0, false, false, 4>(__VA_ARGS__); \
-        }                                                                                                  \
-        if (tier == 2 && tpt == 1) {                                                                       \
-            if (c64) return bounded ? FN<2, 0, 0, true, true, 1>(__VA_ARGS__) : FN<2, 0, 0, false, true, 1>(__VA_ARGS__); \
-            return bounded ? FN<2, 0, 0, true, false, 1>(__VA_ARGS__) : FN<2, 0, 0, false, false, 1>(__VA_ARGS__); \
-        }                                                                                                  \
-        if (tier == 2 && tpt == 4) {                                                                       \
-            if (c64) return bounded ? FN<2, 0, 0, true, true, 4>(__VA_ARGS__) : FN<2, 0, 0, false, true, 4>(__VA_ARGS__); \
-            return bounded ? FN<2, 0, 0, true, false, 4>(__VA_ARGS__) : FN<2, 0, 0, false, false, 4>(__VA_ARGS__); \
         }                                                                                                  \
     } while (0)
 

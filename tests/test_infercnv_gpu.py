@@ -249,6 +249,51 @@ def test_float64_output_matches_oracle_to_1e11():
         np.testing.assert_allclose(stats[:, 1], (want**2).sum(axis=1), rtol=1e-10)
 
 
+@pytest.mark.parametrize(
+    "g,window,step,gene_values",
+    [
+        (58000, 100, 10, False),  # gene axis longer than shared memory (the tutorial dataset's var): staged in parts
+        (12000, 100, 1, False),   # K > 28 tiles of tasks: CTA-per-row median
+        (58000, 250, 1, True),    # both, K*8 beyond shared memory, plus the per-gene layer on the same paths
+        (9000, 37, 7, True),      # step does not divide the window, odd window
+    ],
+)
+def test_general_fallback_kernels_match_oracle(g, window, step, gene_values):
+    """Direct-form smoothing in parts + wide-row centring (csrc/icnv_direct.cu) against the oracle."""
+    n = 5
+    var = cnv.datasets.synthetic_var(g, seed=11, with_extras=True)
+    X = cnv.datasets.synthetic_counts(n, g, seed=g + window)
+    ref = X.mean(axis=0, dtype=np.float64).astype(np.float32)
+    adata = _adata(X, var)
+    chr_pos, res, per_gene = cnv.tl.infercnv(
+        adata, reference=ref, window_size=window, step=step, chunksize=3, inplace=False,
+        calculate_gene_values=gene_values,
+    )
+    out = orc.infercnv(
+        X, var["chromosome"].values, var["start"].values, reference=ref, window_size=window, step=step, chunksize=3,
+        calculate_gene_values=gene_values,
+    )
+    assert {k: int(v) for k, v in chr_pos.items()} == {k: int(v) for k, v in out[0].items()}
+    _compare_thresholded(res.toarray(), out[1].toarray(), 3, what=f"g={g} window={window} step={step}")
+    if gene_values:
+        _compare_gene_layer(per_gene, out[2], 3, f"gene layer g={g} window={window} step={step}")
+    # float64 output of the same path, no filter: 1e-11
+    torch = _torch()
+    from infercnvpy_b200._engine import DevicePlan
+    from infercnvpy_b200._layout import build_layout
+
+    dev = torch.device("cuda", 0)
+    with DevicePlan(build_layout(var, window, step), dev) as plan:
+        plan.set_reference(torch.from_numpy(ref[None, :]).to(dev))
+        assert plan.tier in (1, 2)
+        got = plan.center(plan.smooth(torch.from_numpy(X).to(dev), 3.0), out_dtype=torch.float64)[0].cpu().numpy()
+    want = orc.infercnv(
+        X, var["chromosome"].values, var["start"].values, reference=ref, window_size=window, step=step,
+        dynamic_threshold=None,
+    )[1].toarray()
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-13 * np.abs(want).max())
+
+
 def test_reference_known_answers(full_mock, x_res_actual):
     """/root/reference/tests/test_tools.py:143-191 through the public API (integer matrix, CSR, 2 chunks)."""
     X, var = full_mock
