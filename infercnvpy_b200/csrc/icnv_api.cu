@@ -86,10 +86,23 @@ struct icnv_plan {
     int32_t gs = 0, NG = 0, NGpad = 0, NQ = 0, qstar = -1, Gpad = 0;
     uint32_t raw_base = 0;
     int32_t n_tasks_g = 0;
-    DevBuf<uint32_t> off_w;  // [warp-block][j][lane][u] byte offsets into the staged row
-    DevBuf<int32_t> cols_w;  // same layout, column index, pad = -1 (input of the bounds kernel)
-    DevBuf<int32_t> grp_w;   // [warp-block][lane][u] group whose partial sums this slot produces
-    DevBuf<float> lo_w, hi_w;
+    // gather tables in the order a kernel with unit width uw walks them ([unit][step][lane][u < uw]).  Set 0 serves the
+    // kernel chosen for dense input; when that is the row-pair kernel (uw = 4), set 1 (uw = 2) serves the single-row
+    // kernel that CSR input runs (densify-on-load has no TMA to overlap, two CTAs per SM hide its barriers better).
+    struct GatherTables {
+        int uw = 0;
+        DevBuf<uint32_t> off_w;  // shared-window byte address of the gene (| element position << 24 when permuted)
+        DevBuf<int32_t> cols_w;  // same layout, column index, pad = -1 (input of the bounds kernel)
+        DevBuf<int32_t> grp_w;   // [unit][lane][u] group whose partial sums this slot produces
+        DevBuf<float> lo_w, hi_w;
+        void release() {
+            off_w.release();
+            cols_w.release();
+            grp_w.release();
+            lo_w.release();
+            hi_w.release();
+        }
+    } tab[2];
     DevBuf<double> alpha, beta, cw;
     DevBuf<Task> tasks_g;
 
@@ -123,11 +136,8 @@ struct icnv_plan {
     DevBuf<double> gv_scratch;
 
     ~icnv_plan() {
-        off_w.release();
-        cols_w.release();
-        grp_w.release();
-        lo_w.release();
-        hi_w.release();
+        tab[0].release();
+        tab[1].release();
         alpha.release();
         beta.release();
         cw.release();
@@ -416,7 +426,6 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         // the kernel that will run decides the unit width: row pairs (templated window 100 that fits twice) walk whole
         // warp-blocks, everything else half warp-blocks
         const bool pairs = p->permuted && smooth_rows_default() == 2 && smem_grouped(*p, 0, 2) <= SMEM_MAX;
-        const int uw = ICNV_UNIT_WIDTH(pairs ? 2 : 1);
         p->rows = pairs ? 2 : 1;
         uint32_t raw_base = 0;
         if (smooth_raw_base(&raw_base)) return ICNV_ECUDA;
@@ -425,6 +434,8 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             set_error("internal: shared window address does not fit the table entry");
             return ICNV_EINVAL;
         }
+        for (int ts = 0; ts < (pairs ? 2 : 1); ++ts) {
+        const int uw = ts == 0 ? ICNV_UNIT_WIDTH(pairs ? 2 : 1) : ICNV_UNIT_WIDTH(1);
         std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
         std::vector<int32_t> cols(n_entries, -1);
         std::vector<int32_t> grp((size_t)n_wb * 32 * 4, p->NGpad);  // empty slots store their zeros to a pad group
@@ -447,10 +458,12 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
                         if (p->permuted) off[e] |= (uint32_t)j << 24;  // pads carry their j too (x = 0 either way)
                     }
                 }
-        if (p->off_w.upload(off) || p->cols_w.upload(cols) || p->grp_w.upload(grp) || p->alpha.upload(alpha) || p->beta.upload(beta) ||
-            p->cw.upload(cw) || p->tasks_g.upload(tasks))
+        auto& T = p->tab[ts];
+        T.uw = uw;
+        if (T.off_w.upload(off) || T.cols_w.upload(cols) || T.grp_w.upload(grp) || T.lo_w.alloc(n_entries) || T.hi_w.alloc(n_entries))
             return ICNV_ECUDA;
-        if (p->lo_w.alloc(n_entries) || p->hi_w.alloc(n_entries)) return ICNV_ECUDA;
+        }  // table sets
+        if (p->alpha.upload(alpha) || p->beta.upload(beta) || p->cw.upload(cw) || p->tasks_g.upload(tasks)) return ICNV_ECUDA;
     }
     if (flat_inv.empty()) flat_inv.push_back(1.0);
     if (p->flat_inv.upload(flat_inv)) return ICNV_ECUDA;
@@ -596,8 +609,10 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
     int rc = choose(*plan, c64, &ch);
     if (rc) return rc;
     if (ch.tier < 2) {
-        rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->cols_w.ptr, (int64_t)plan->cols_w.n, plan->lo_w.ptr,
-                              plan->hi_w.ptr, false, st);
+        for (int ts = 0; ts < 2 && !rc; ++ts)
+            if (plan->tab[ts].uw)
+                rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->tab[ts].cols_w.ptr, (int64_t)plan->tab[ts].cols_w.n,
+                                      plan->tab[ts].lo_w.ptr, plan->tab[ts].hi_w.ptr, false, st);
     } else {
         rc = aux_build_bounds(ref, c64, n_cat, plan->G, plan->idx_lin.ptr, plan->n_sorted, plan->lo_lin.ptr,
                               plan->hi_lin.ptr, c64, st);
@@ -676,11 +691,17 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
     sp.NGpad = plan->NGpad;
     sp.NQ = plan->NQ;
     sp.qstar = plan->qstar;
-    sp.off_w = plan->off_w.ptr;
+    // CSR input runs the single-row kernel (two CTAs per SM) even when dense input takes row pairs
+    if (ch.tier == 0 && ch.rows == 2 && !sp.X && plan->tab[1].uw) {
+        ch.rows = 1;
+        ch.smem = smem_grouped(*plan, 0, 1);
+    }
+    const auto& T = plan->tab[(ch.tier == 0 && plan->rows == 2 && ch.rows == 1) ? 1 : 0];
+    sp.off_w = T.off_w.ptr;
     sp.raw_base = plan->raw_base;
-    sp.grp_w = plan->grp_w.ptr;
-    sp.lo_w = plan->lo_w.ptr;
-    sp.hi_w = plan->hi_w.ptr;
+    sp.grp_w = T.grp_w.ptr;
+    sp.lo_w = T.lo_w.ptr;
+    sp.hi_w = T.hi_w.ptr;
     sp.alpha = plan->alpha.ptr;
     sp.beta = plan->beta.ptr;
     sp.cw = plan->cw.ptr;
