@@ -296,12 +296,18 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                                 d = xv - l4[u];
                             d = fminf(fmaxf(d, -clipf), clipf);
                             const double dd = (double)d;
-                            a[rr][u] += dd;
-                            if constexpr (PERM)
-                                b[rr][u] = fma(jd[u], dd, b[rr][u]);
-                            else if (j > 0)
-                                b[rr][u] = fma((double)j, dd, b[rr][u]);
-                            if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
+                            if (TIER == 0 && j == 0) {  // first step of the (unrolled) walk: no add to zero
+                                a[rr][u] = dd;
+                                if constexpr (PERM) b[rr][u] = jd[u] * dd;
+                                if (qstar >= 0) c[rr][u] = cwj * dd;
+                            } else {
+                                a[rr][u] += dd;
+                                if constexpr (PERM)
+                                    b[rr][u] = fma(jd[u], dd, b[rr][u]);
+                                else if (j > 0)
+                                    b[rr][u] = fma((double)j, dd, b[rr][u]);
+                                if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
+                            }
                         }
                 };
                 if constexpr (TIER == 0) {
