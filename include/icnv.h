@@ -183,6 +183,13 @@ int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* thread
  * gather schedule (1.0 = conflict-free; csrc/icnv_schedule.cu).  0 when the plan has no grouped layout. */
 int icnv_plan_gather_cost(const icnv_plan* plan, double* wavefronts_per_gather);
 
+/* Host-only (no device needed): the gather schedule of csrc/icnv_schedule.cu on a caller-supplied group table
+ * gcol [n_groups, gs] (matrix column of every group element, -1 = pad).  Fills slot_group_out [nsets*32] (group of every
+ * lane slot, -1 = none) and order_out [nsets*32*gs] (element read at every step); returns wavefronts per gather, < 0 if
+ * nsets*32 slots cannot hold the groups.  Used by the CPU tests. */
+double icnv_host_schedule_gathers(const int32_t* gcol, int32_t n_groups, int32_t gs, int32_t n_genes, int32_t nsets,
+                                  int32_t permute, int32_t* slot_group_out, uint8_t* order_out);
+
 /* Developer aid (tools/timeline.py): when dev_buf != NULL the smoothing kernel writes clock64 stamps
  * [grid][rows_per_cta][16] for the first rows_per_cta rows of every CTA.  NULL switches it off. */
 int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta);

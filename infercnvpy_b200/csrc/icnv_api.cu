@@ -705,13 +705,6 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
     sp.alpha = plan->alpha.ptr;
     sp.beta = plan->beta.ptr;
     sp.cw = plan->cw.ptr;
-    sp.window = plan->window;
-    sp.step = plan->step;
-    sp.n_sorted = plan->n_sorted;
-    sp.idx_lin = plan->idx_lin.ptr;
-    sp.lo_lin = plan->lo_lin.ptr;
-    sp.hi_lin = plan->hi_lin.ptr;
-    sp.wdir = plan->wdir.ptr;
     sp.clip = plan->c64 ? lfc_clip : (double)(float)lfc_clip;
     sp.clipf = (float)lfc_clip;
     sp.inv_sumw = plan->inv_sumw;

@@ -66,14 +66,6 @@ struct SmoothParams {
     const double* alpha;    // [NQ] weight of A_g = sum_j x
     const double* beta;     // [NQ] weight of B_g = sum_j j*x
     const double* cw;       // [gs] weights inside the peak group (C_g = sum_j cw_j x)
-    // ---- direct tier (2)
-    int32_t window;
-    int32_t step;
-    int32_t n_sorted;       // genes in position order, all segments
-    const int32_t* idx_lin; // [n_sorted]
-    const void* lo_lin;     // [n_sorted] float or double (C64)
-    const void* hi_lin;
-    const double* wdir;     // [window] pyramid weights
     // ---- common
     double clip;
     float clipf;

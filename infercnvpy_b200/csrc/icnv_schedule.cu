@@ -272,3 +272,15 @@ double schedule_gathers(const std::vector<int32_t>& gcol, int NG, int gs, int n_
 }
 
 }  // namespace icnv
+
+// Host-only test hook (no device, no CUDA call): runs the schedule on a caller-supplied group table so that the CPU test
+// suite can check its invariants.  slot_group_out [nsets*32], order_out [nsets*32*gs] (may be NULL).
+extern "C" double icnv_host_schedule_gathers(const int32_t* gcol, int32_t n_groups, int32_t gs, int32_t n_genes, int32_t nsets,
+                                             int32_t permute, int32_t* slot_group_out, uint8_t* order_out) {
+    std::vector<int32_t> g(gcol, gcol + (size_t)n_groups * gs), slot;
+    std::vector<uint8_t> order;
+    const double cost = icnv::schedule_gathers(g, n_groups, gs, n_genes, nsets, permute != 0, slot, order);
+    if (slot_group_out) std::copy(slot.begin(), slot.end(), slot_group_out);
+    if (order_out) std::copy(order.begin(), order.end(), order_out);
+    return cost;
+}

@@ -80,3 +80,62 @@ def test_duck_anndata_slicing():
     b = a[:, np.arange(30) % 2 == 0]
     assert b.shape == (2, 15) and list(b.var_names) == list(var.index[::2])
     assert a.copy().X is not a.X
+
+
+def _group_table(var, window, step):
+    """Position-ordered groups of `step` genes per chromosome, like icnv_plan_create builds them."""
+    lay = build_layout(var, window, step)
+    rows = []
+    for c in range(len(lay.chromosomes)):
+        s0, s1 = int(lay.seg_off[c]), int(lay.seg_off[c + 1])
+        g_c = s1 - s0
+        flat = not (window < g_c)
+        n_out = 1 if flat else (g_c - window) // step + 1
+        n_grp = -(-g_c // step) if flat else ((n_out - 1) * step + window) // step
+        for g in range(n_grp):
+            rows.append([lay.gene_idx[s0 + g * step + j] if g * step + j < g_c else -1 for j in range(step)])
+    return np.asarray(rows, dtype=np.int32), var.shape[0]
+
+
+@pytest.mark.parametrize("g,sort_in_memory", [(20000, False), (20000, True), (2400, False)])
+def test_gather_schedule_invariants(g, sort_in_memory):
+    """csrc/icnv_schedule.cu on the host: every group gets exactly one lane slot (lane % 8 == group % 8), every lane's
+    walk is a permutation of its group, and the permuted walk costs far fewer shared-memory wavefronts than the
+    natural one (the kernel itself only decodes what this produces; GPU parity tests cover the arithmetic)."""
+    lib = _lib.load()
+    var = cnv.datasets.synthetic_var(g, seed=0)
+    if sort_in_memory:
+        var = var.sort_values(["chromosome", "start"])
+    gcol, n_genes = _group_table(var, 100, 10)
+    n_groups, gs = gcol.shape
+    nsets = -(-(-(-n_groups // 4)) // 32) * 4
+    cost = {}
+    for permute in (0, 1):
+        slot = np.empty(nsets * 32, dtype=np.int32)
+        order = np.empty(nsets * 32 * gs, dtype=np.uint8)
+        cost[permute] = lib.icnv_host_schedule_gathers(
+            gcol.ctypes.data_as(_lib.c_i32p), n_groups, gs, n_genes, nsets, permute,
+            slot.ctypes.data_as(_lib.c_i32p), order.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+        )
+        used = slot[slot >= 0]
+        assert sorted(used.tolist()) == list(range(n_groups))
+        lanes = np.flatnonzero(slot >= 0) % 32
+        assert np.all(lanes % 8 == used % 8)
+        walks = order.reshape(nsets * 32, gs)[slot >= 0]
+        assert np.all(np.sort(walks, axis=1) == np.arange(gs))
+        if not permute:
+            assert np.all(walks == np.arange(gs))
+        # recompute the cost independently: distinct words per bank, the pad word counted once in bank n_genes % 32
+        total = 0
+        for s in range(nsets):
+            grp = slot[s * 32 : (s + 1) * 32]
+            for t in range(gs):
+                cols = np.array([gcol[grp[l], order[(s * 32 + l) * gs + t]] if grp[l] >= 0 else -1 for l in range(32)])
+                cnt = np.bincount(cols[cols >= 0] & 31, minlength=32)
+                if (cols < 0).any():
+                    cnt[n_genes & 31] += 1
+                total += max(1, int(cnt.max()))
+        assert cost[permute] == pytest.approx(total / (nsets * gs), rel=1e-12)
+    assert cost[1] < 1.5 and cost[1] < 0.75 * cost[0]
+    # too few slots -> refused
+    assert lib.icnv_host_schedule_gathers(gcol.ctypes.data_as(_lib.c_i32p), n_groups, gs, n_genes, 4, 1, None, None) < 0
