@@ -199,7 +199,7 @@ def main():
         "dynamic_threshold": DYN,
         "reference": "mean of all cells (computed every step, all-reduced when N>1)",
         "sharding": f"rows, {world} rank(s), shard boundaries multiples of chunksize",
-        "l2": "input 8 GB per GPU per step >> 126 MB L2 (no flush needed)",
+        "l2": f"input {args.cells * G_GENES * 4 / 1e9:.0f} GB per GPU per step >> 126 MB L2 (no flush needed)",
     }
 
     # ---------------- reference arm: the CPU path on the host cores ----------------

@@ -147,6 +147,16 @@ int icnv_rowabs_dense(const void* X, int32_t is_f64, int64_t n_rows, int64_t K, 
 int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_rows, int32_t n_labels,
                     double* label_sum, int64_t* label_rows, void* stream);
 
+/* ------------------------------------------------------------ ITH scores ----
+ * tl/_scores.py:77-221 (ithgex :130-141, ithcna :203-214): np.corrcoef over the rows (cells) of ONE group.
+ *   X     [n_rows, ld >= K] float64 row-major, the group's dense block
+ *   corr  [n_rows, ldc >= n_rows] float64, OVERWRITTEN: Pearson correlation of every pair of rows, clipped to
+ *         [-1, 1] like np.corrcoef; rows without variance give NaN
+ *   work  [2 * n_rows] float64 scratch (row means, inverse norms)
+ * The score is the inter-quartile range of ALL n_rows^2 entries (np.percentile, linear interpolation). */
+int icnv_row_corrcoef_f64(const double* X, int64_t n_rows, int64_t ld, int32_t K, double* corr, int64_t ldc, double* work,
+                          void* stream);
+
 /* --------------------------------------------- pca / neighbors / leiden ----
  * The reference hands these steps to scanpy (tl/__init__.py:13-75, pp/__init__.py:8-43 ->
  * scikit-learn TruncatedSVD(arpack), exact/approximate kNN + umap-learn fuzzy_simplicial_set,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "icnv_dense_to_csr": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
     "icnv_rowabs_csr": (C.c_int, [c_vp, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_rowabs_dense": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp]),
+    "icnv_row_corrcoef_f64": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32, c_vp, C.c_int64, c_vp, c_vp]),
     "icnv_csr_to_dense_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, C.c_int64, C.c_int32, c_vp, C.c_int64, c_vp]),
     "icnv_gram_f32": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32, c_vp, c_vp]),
     "icnv_project_f32": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32, c_vp, C.c_int32, c_vp, c_vp, c_vp]),

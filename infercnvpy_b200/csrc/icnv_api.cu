@@ -34,6 +34,7 @@ int aux_rowabs_csr(const int64_t*, const void*, bool, int64_t, double*, cudaStre
 int aux_rowabs_dense(const void*, bool, int64_t, int64_t, int64_t, double*, cudaStream_t);
 int aux_label_sums(const double*, const int32_t*, int64_t, int, double*, int64_t*, cudaStream_t);
 size_t smooth_scratch_bytes();
+int aux_row_corrcoef(const double*, int64_t, int64_t, int, double*, int64_t, double*, cudaStream_t);
 int graph_csr_to_dense(const int64_t*, const int32_t*, const void*, bool, int64_t, int, float*, int64_t, cudaStream_t);
 int graph_gram(const float*, int64_t, int64_t, int, double*, cudaStream_t);
 int graph_project(const float*, int64_t, int64_t, int, const double*, int, const double*, float*, cudaStream_t);
@@ -889,6 +890,19 @@ int icnv_label_sums(const double* row_abs_sum, const int32_t* labels, int64_t n_
                     int64_t* label_rows, void* stream) {
     if (!row_abs_sum || !labels || !label_sum || !label_rows) return ICNV_EINVAL;
     return aux_label_sums(row_abs_sum, labels, n_rows, n_labels, label_sum, label_rows, (cudaStream_t)stream);
+}
+
+int icnv_row_corrcoef_f64(const double* X, int64_t n_rows, int64_t ld, int32_t K, double* corr, int64_t ldc, double* work,
+                          void* stream) {
+    if (!X || !corr || !work || n_rows < 0 || K < 1 || ld < K || ldc < n_rows) {
+        set_error("icnv_row_corrcoef_f64: bad argument");
+        return ICNV_EINVAL;
+    }
+    if ((n_rows + 63) / 64 > 60000) {
+        set_error("icnv_row_corrcoef_f64: group too large");
+        return ICNV_EUNSUPPORTED;
+    }
+    return aux_row_corrcoef(X, n_rows, ld, K, corr, ldc, work, (cudaStream_t)stream);
 }
 
 int icnv_csr_to_dense_f32(const int64_t* indptr, const int32_t* indices, const void* data, int32_t data_is_f64, int64_t n_rows,

@@ -693,6 +693,92 @@ __global__ void __launch_bounds__(256) label_sums_kernel(const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// ITH scores: /root/reference/src/infercnvpy/tl/_scores.py:77-221 — np.corrcoef over the ROWS (cells) of one group.
+// row_center_kernel: per row the mean and 1/sqrt(sum (x - mean)^2) (warp per row, two passes, fp64);
+// row_corr_kernel: 64x64 tiles of cells (upper triangle, mirrored), fp64 FMAs over the features, then
+// c_ij * inv_i * inv_j clipped to [-1, 1] like np.corrcoef; a row without variance gives 0 * inf = NaN like numpy's 0/0.
+__global__ void __launch_bounds__(256) row_center_kernel(const double* __restrict__ X, int64_t n, int64_t ld, int K,
+                                                         double* __restrict__ mean, double* __restrict__ inv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += n_warps) {
+        const double* row = X + r * ld;
+        double s = 0.0;
+        for (int c = lane; c < K; c += 32) s += row[c];
+        s = warp_sum_dd(s);
+        const double m = s / (double)K;
+        double ss = 0.0;
+        for (int c = lane; c < K; c += 32) {
+            const double d = row[c] - m;
+            ss = fma(d, d, ss);
+        }
+        ss = warp_sum_dd(ss);
+        if (lane == 0) {
+            mean[r] = m;
+            inv[r] = 1.0 / sqrt(ss);
+        }
+    }
+}
+
+constexpr int CT = 64;  // tile edge (cells)
+constexpr int CR = 16;  // features per shared-memory chunk
+__global__ void __launch_bounds__(256) row_corr_kernel(const double* __restrict__ X, int64_t n, int64_t ld, int K,
+                                                       const double* __restrict__ mean, const double* __restrict__ inv,
+                                                       double* __restrict__ C, int64_t ldc) {
+    __shared__ double As[CR][CT + 1], Bs[CR][CT + 1];
+    const int nt = (int)((n + CT - 1) / CT);
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= nt - ti) {
+        rem -= nt - ti;
+        ++ti;
+    }
+    const int tj = ti + rem;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += CR) {
+        for (int e = threadIdx.x; e < CR * CT; e += 256) {
+            const int c = e / CR, r = e % CR;  // consecutive threads walk the features of one cell
+            const int64_t ra = (int64_t)ti * CT + c, rb = (int64_t)tj * CT + c;
+            const int k = k0 + r;
+            As[r][c] = (ra < n && k < K) ? X[ra * ld + k] - mean[ra] : 0.0;
+            Bs[r][c] = (rb < n && k < K) ? X[rb * ld + k] - mean[rb] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < CR; ++r) {
+            double a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[q] = As[r][ty * 4 + q];
+                b[q] = Bs[r][tx * 4 + q];
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t ci = (int64_t)ti * CT + ty * 4 + p, cj = (int64_t)tj * CT + tx * 4 + q;
+            if (ci < n && cj < n) {
+                double v = acc[p][q] * inv[ci] * inv[cj];
+                v = v > 1.0 ? 1.0 : (v < -1.0 ? -1.0 : v);  // NaN stays NaN
+                C[ci * ldc + cj] = v;
+                C[cj * ldc + ci] = v;
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side launch wrappers (called from icnv_api.cu)
 static int grid_for_rows(int64_t n_rows) {
     int64_t g = (n_rows + 7) / 8;  // 8 warps per 256-thread CTA
@@ -874,6 +960,16 @@ int aux_label_sums(const double* row_abs, const int32_t* labels, int64_t n_rows,
                    int64_t* label_rows, cudaStream_t st) {
     if (n_labels <= 0) return 0;
     label_sums_kernel<<<n_labels, 256, 0, st>>>(row_abs, labels, n_rows, label_sum, label_rows);
+    ICNV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int aux_row_corrcoef(const double* X, int64_t n, int64_t ld, int K, double* corr, int64_t ldc, double* work, cudaStream_t st) {
+    if (n == 0) return 0;
+    row_center_kernel<<<grid_for_rows(n), 256, 0, st>>>(X, n, ld, K, work, work + n);
+    ICNV_CUDA(cudaGetLastError());
+    const int64_t nt = (n + CT - 1) / CT;
+    row_corr_kernel<<<(unsigned)(nt * (nt + 1) / 2), 256, 0, st>>>(X, n, ld, K, work, work + n, corr, ldc);
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }

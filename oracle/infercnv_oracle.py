@@ -38,6 +38,7 @@ __all__ = [
     "infercnv_chunk",
     "infercnv",
     "cnv_score",
+    "ith_score",
 ]
 
 
@@ -329,3 +330,27 @@ def cnv_score(X_cnv, labels) -> dict:
     """
     labels = np.asarray(labels)
     return {lab: np.mean(np.abs(X_cnv[labels == lab, :])) for lab in pd.unique(pd.Series(labels))}
+
+
+# --------------------------------------------------------------------------- #
+# ITH scores
+# --------------------------------------------------------------------------- #
+def ith_score(X, labels) -> dict:
+    """tl/_scores.py:128-141 (ithgex) / :201-214 (ithcna) — per label the inter-quartile range of the cell-cell Pearson
+    correlation matrix of its rows (``np.corrcoef(X, rowvar=True)``, all entries, ``np.percentile(.., [75, 25])``).
+
+    ``X`` is the matrix the score is taken of (expression for ithgex, ``obsm["X_cnv"]`` for ithcna), dense or sparse;
+    groups with a single cell are skipped (``:135,208``).
+    """
+    labels = np.asarray(labels)
+    out = {}
+    for lab in pd.unique(pd.Series(labels)):
+        block = X[labels == lab, :]
+        if sp.issparse(block):
+            block = block.todense()
+        if block.shape[0] <= 1:
+            continue
+        pcorr = np.corrcoef(block, rowvar=True)
+        q75, q25 = np.percentile(pcorr, [75, 25])
+        out[lab] = q75 - q25
+    return out

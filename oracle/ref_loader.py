@@ -56,13 +56,22 @@ class MiniAnnData:
 
     def __getitem__(self, key):
         rows, cols = key
-        assert isinstance(rows, slice) and rows == slice(None)
-        cols = np.asarray(cols)
+        if isinstance(rows, slice) and rows == slice(None):  # adata[:, gene_mask]  (_infercnv.py:110)
+            cols = np.asarray(cols)
+            return MiniAnnData(
+                self.X[:, cols],
+                obs=self.obs,
+                var=self.var.loc[cols],
+                layers={k: v[:, cols] for k, v in self.layers.items()},
+            )
+        assert isinstance(cols, slice) and cols == slice(None)  # adata[cell_mask, :]  (_scores.py:131,204)
+        rows = np.asarray(rows)
         return MiniAnnData(
-            self.X[:, cols],
-            obs=self.obs,
-            var=self.var.loc[cols],
-            layers={k: v[:, cols] for k, v in self.layers.items()},
+            self.X[rows],
+            obs=self.obs.loc[rows],
+            var=self.var,
+            layers={k: v[rows] for k, v in self.layers.items()},
+            obsm={k: v[rows] for k, v in self.obsm.items()},
         )
 
 

@@ -7,6 +7,8 @@ and with float64 output 1e-11.  Entries the noise filter keeps on one side and z
 ("flips") are only legal if the value sits within float32 rounding of the chunk threshold.
 """
 
+from pathlib import Path
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -443,3 +445,46 @@ def test_cnv_score_known_answer_and_golden(golden_loader):
     res = cnv.tl.cnv_score(a, "grp", inplace=False)
     for k, v in zip(gold["score_keys"].tolist(), gold["score_vals"].tolist()):
         assert float(res[k]) == pytest.approx(v, rel=1e-12)
+
+
+# ---- ITH scores (tl/_scores.py:77-221) --------------------------------------------------------------
+def test_ith_scores_known_answers_and_golden():
+    from tests.golden.make_golden_ith import ith_case
+    from tests.test_oracle_golden import ITH_CNV, ITH_EXPR, ITH_GROUPS
+
+    # /root/reference/tests/test_scores.py:6-15
+    obs = pd.DataFrame({"group": ITH_GROUPS}, index=[f"c{i}" for i in range(8)])
+    for container in (np.array, sp.csr_matrix, sp.csc_matrix):
+        a = cnv.AnnData(container(ITH_EXPR), obs=obs.copy(), obsm={"X_cnv": container(ITH_CNV)})
+        gex = cnv.tl.ithgex(a, "group", inplace=False)
+        assert gex["A"] == 0 and gex["B"] == pytest.approx(1.2628, abs=0.001)
+        cna = cnv.tl.ithcna(a, "group", inplace=False)
+        assert cna["A"] == pytest.approx(1.053, abs=0.001) and cna["B"] == 0
+        cnv.tl.ithgex(a, "group")
+        cnv.tl.ithcna(a, "group")
+        np.testing.assert_allclose(a.obs["ithgex"].values, [gex["A"]] * 5 + [gex["B"]] * 3)
+        np.testing.assert_allclose(a.obs["ithcna"].values, [cna["A"]] * 5 + [cna["B"]] * 3)
+    with pytest.raises(ValueError, match="both layer and raw"):
+        cnv.tl.ithgex(a, "group", use_raw=True, layer="x")
+    # outputs of the unmodified reference on a seeded 260-cell case (tests/golden/make_golden_ith.py)
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ith_scores.npz", allow_pickle=False)
+    expr, x_cnv, labels = ith_case()
+    obs = pd.DataFrame({"patient": labels}, index=[f"c{i}" for i in range(len(labels))])
+    a = cnv.AnnData(expr, obs=obs, obsm={"X_cnv": x_cnv})
+    gex = cnv.tl.ithgex(a, "patient", inplace=False)
+    cna = cnv.tl.ithcna(a, "patient", inplace=False)
+    assert sorted(gex) == z["keys"].tolist() == sorted(cna)
+    for k, g, c in zip(z["keys"].tolist(), z["ithgex"].tolist(), z["ithcna"].tolist()):
+        assert float(gex[k]) == pytest.approx(g, rel=1e-9) and float(cna[k]) == pytest.approx(c, rel=1e-9)
+    with pytest.raises(KeyError):  # the one-cell group has no score to broadcast (_scores.py:144-146)
+        cnv.tl.ithgex(a, "patient")
+    # a cell without variance poisons its group with NaN, like np.corrcoef / np.percentile
+    flat = expr.copy()
+    flat[3] = 0.25
+    b = cnv.AnnData(flat, obs=obs.copy())
+    res = cnv.tl.ithgex(b, "patient", inplace=False)
+    want = orc.ith_score(flat, labels)
+    for k in want:
+        assert np.isnan(res[k]) == np.isnan(want[k])
+        if not np.isnan(want[k]):
+            assert float(res[k]) == pytest.approx(float(want[k]), rel=1e-9)

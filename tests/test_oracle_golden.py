@@ -238,3 +238,31 @@ def test_oracle_vs_live_reference_random(seed):
     )
     assert {k: int(v) for k, v in chr_pos_r.items()} == {k: int(v) for k, v in chr_pos_o.items()}
     np.testing.assert_array_equal(sp.csr_matrix(res_r).toarray(), res_o.toarray())
+
+
+# ---- ITH scores (tl/_scores.py:77-221) --------------------------------------------------------------
+ITH_EXPR = np.array([[1, 1, 1, 1, 1, 1, 2, 3], [2, 2, 2, 2, 2, 2, 8, 0], [3, 3, 3, 3, 3, 10, 3, 7]]).T
+ITH_CNV = np.array([[1, 1, 1, 2, 2, 1, 1, 1], [2, 2, 2, 1, 1, 2, 2, 2], [4, 4, 4, 2, 2, 3, 3, 3], [2, 2, 2, 4, 4, 4, 4, 4]]).T
+ITH_GROUPS = list("AAAAABBB")
+
+
+@pytest.mark.parametrize("container", [np.array, sp.csr_matrix, sp.csc_matrix])
+def test_ith_scores_reference_known_answers(container):
+    # /root/reference/tests/test_scores.py:6-15 on /root/reference/tests/conftest.py:111-139
+    gex = orc.ith_score(container(ITH_EXPR), ITH_GROUPS)
+    assert gex["A"] == 0 and gex["B"] == pytest.approx(1.2628, abs=0.001)
+    cna = orc.ith_score(container(ITH_CNV), ITH_GROUPS)
+    assert cna["A"] == pytest.approx(1.053, abs=0.001) and cna["B"] == 0
+
+
+def test_ith_scores_match_reference_golden():
+    from tests.golden.make_golden_ith import ith_case
+
+    from tests.conftest import GOLDEN
+
+    z = np.load(GOLDEN / "ith_scores.npz", allow_pickle=False)
+    expr, x_cnv, labels = ith_case()
+    gex, cna = orc.ith_score(expr, labels), orc.ith_score(x_cnv, labels)
+    assert sorted(gex) == z["keys"].tolist() and "solo" not in gex
+    for k, g, c in zip(z["keys"].tolist(), z["ithgex"].tolist(), z["ithcna"].tolist()):
+        assert float(gex[k]) == g and float(cna[k]) == c  # same numpy calls: bit-identical
