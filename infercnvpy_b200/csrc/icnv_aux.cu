@@ -769,9 +769,9 @@ __global__ void __launch_bounds__(256) row_corr_kernel(const double* __restrict_
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int64_t ci = (int64_t)ti * CT + ty * 4 + p, cj = (int64_t)tj * CT + tx * 4 + q;
-            if (ci < n && cj < n) {
-                double v = acc[p][q] * inv[ci] * inv[cj];
-                v = v > 1.0 ? 1.0 : (v < -1.0 ? -1.0 : v);  // NaN stays NaN
+            if (ci < n && cj < n && ci <= cj) {  // diagonal tiles: one writer per symmetric pair
+                double v = acc[p][q] * (inv[ci] * inv[cj]);
+                if (!isnan(v)) v = fmin(fmax(v, -1.0), 1.0);  // np.clip keeps NaN (fmin / fmax would drop it)
                 C[ci * ldc + cj] = v;
                 C[cj * ldc + ci] = v;
             }

@@ -56,10 +56,10 @@ def _group_iqr(block: np.ndarray, device) -> float:
         lib.icnv_row_corrcoef_f64(_lib.ptr(X), n, X.stride(0), K, _lib.ptr(corr), corr.stride(0), _lib.ptr(work), _lib.stream_handle(device)),
         "icnv_row_corrcoef_f64",
     )
-    flat = torch.sort(corr.reshape(-1)).values  # NaN sorts last
-    del corr
-    if bool(torch.isnan(flat[-1]).item()):  # np.percentile of an array with a NaN is NaN
+    if bool(torch.isnan(corr).any().item()):  # np.percentile of an array with a NaN is NaN
         return float("nan")
+    flat = torch.sort(corr.reshape(-1)).values
+    del corr
     q75 = _np_linear_quantile(flat, n * n, 0.75)
     q25 = _np_linear_quantile(flat, n * n, 0.25)
     return q75 - q25

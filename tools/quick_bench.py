@@ -28,6 +28,8 @@ def timeit(fn, reps=None, warm=2):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
+    if os.environ.get("QB_TRACE"):
+        print("trace", [round(t, 3) for t in ts])
     return min(ts), float(np.median(ts))
 
 # box sanity: plain device copy bandwidth (read + write), to spot a slow box
