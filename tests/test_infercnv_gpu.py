@@ -427,6 +427,71 @@ def test_properties_at_scale():
     assert torch.equal(o4, pre[:2000])
 
 
+def test_properties_at_full_bench_size():
+    """BASELINE configs[1] at full size (100 000 cells x 20 000 genes fp32, window 100, chunks of 5000): properties that
+    need no oracle — bit-reproducibility, shard invariance, exact medians, thresholds, statistics."""
+    torch = _torch()
+    from infercnvpy_b200._engine import DevicePlan
+    from infercnvpy_b200._layout import build_layout
+
+    dev = torch.device("cuda", 0)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 24 << 30:
+        pytest.skip("needs 24 GiB of free device memory")
+    G, N, chunk = 20000, 100_000, 5000
+    var = cnv.datasets.synthetic_var(G, seed=0)
+    Xd = cnv.datasets.device_counts(N, G, dev, seed=4321)
+    with DevicePlan(build_layout(var, 100, 10), dev) as plan:
+        sums, counts = plan.colsum(Xd)
+        # the reference profile is the column mean (fp64 sums): check a strided sample of columns against torch
+        cols = torch.arange(0, G, 97, device=dev)
+        want_mean = Xd[:, cols].double().mean(dim=0)
+        ref = plan.mean_from_sums(sums, counts)
+        assert int(counts[0]) == N
+        torch.testing.assert_close(ref[0, cols].double(), want_mean, rtol=1e-6, atol=1e-9)
+        plan.set_reference(ref)
+        tmp = plan.smooth(Xd, 3.0)
+        pre, stats = plan.center(tmp)
+        # (1) bit-reproducible from launch to launch (dynamic work hand-out must not change a single bit)
+        tmp2 = plan.smooth(Xd, 3.0)
+        assert torch.equal(tmp2.view(torch.int64), tmp.view(torch.int64))
+        pre2, stats2 = plan.center(tmp2)
+        assert torch.equal(pre2, pre) and torch.equal(stats2, stats)
+        del tmp2, pre2, stats2
+        # (2) row shards cut at chunk boundaries give the same matrix (what the multi-GPU path relies on)
+        cut = 35_000
+        top = plan.center(plan.smooth(Xd[:cut], 3.0))[0]
+        assert torch.equal(top, pre[:cut])
+        bottom = plan.center(plan.smooth(Xd[cut:], 3.0))[0]
+        assert torch.equal(bottom, pre[cut:])
+        del top, bottom
+        # (3) every row is centred on its exact median (even K: mean of the middle pair), checked on 4000 sampled rows
+        rows = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(1))[:4000]
+        srt = pre[rows].double().sort(dim=1).values
+        mid = 0.5 * (srt[:, plan.K // 2 - 1] + srt[:, plan.K // 2])
+        assert float(mid.abs().max()) < 1e-7
+        # (4) per-chunk threshold = 1.5 * population std of the chunk; kept entries are never below it
+        out = pre.clone()
+        thr, row_abs, row_nnz = plan.threshold(out, stats, chunk, 1.5)
+        assert thr.numel() == N // chunk
+        for c in (0, 7, 19):
+            blk = pre[c * chunk : (c + 1) * chunk].double()
+            want = 1.5 * blk.std(unbiased=False).item()
+            assert abs(thr[c].item() - want) / want < 1e-6
+            kept = out[c * chunk : (c + 1) * chunk]
+            assert float(kept[kept != 0].abs().min()) >= thr[c].item() * (1 - 1e-6)
+            assert torch.equal(kept != 0, blk.abs() >= thr[c])  # strict `<` of _infercnv.py:451, compared in float64
+        # (5) statistics and CSR round trip over the whole matrix
+        np.testing.assert_allclose(row_abs.cpu().numpy(), out.double().abs().sum(dim=1).cpu().numpy(), rtol=1e-12)
+        assert torch.equal(row_nnz.long(), (out != 0).sum(dim=1))
+        indptr, indices, data = plan.to_csr(out, row_nnz)
+        assert int(indptr[-1]) == int(row_nnz.sum()) and 0.05 < int(indptr[-1]) / out.numel() < 0.3
+        r = 54_321
+        dense_row = torch.zeros(plan.K, device=dev)
+        dense_row[indices[indptr[r] : indptr[r + 1]].long()] = data[indptr[r] : indptr[r + 1]]
+        assert torch.equal(dense_row, out[r])
+
+
 def test_cnv_score_known_answer_and_golden(golden_loader):
     # /root/reference/tests/test_scores.py:18-21
     X_cnv = np.array([[1, 1, 1, 2, 2, 1, 1, 1], [2, 2, 2, 1, 1, 2, 2, 2], [4, 4, 4, 2, 2, 3, 3, 3], [2, 2, 2, 4, 4, 4, 4, 4]]).T
