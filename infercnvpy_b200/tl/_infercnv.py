@@ -21,8 +21,14 @@ log = logging.getLogger("infercnvpy_b200")
 
 def _block_rows(n_rows: int, n_genes: int, n_out: int, chunksize: int, gene_values: bool = False) -> int:
     """Rows per device block: a multiple of ``chunksize`` (so every per-chunk std sees a whole
-    chunk, _infercnv.py:123,450) that keeps input + output under ICNV_BLOCK_BYTES (default 16 GiB)."""
-    budget = int(os.environ.get("ICNV_BLOCK_BYTES", 16 << 30))
+    chunk, _infercnv.py:123,450) that keeps input + intermediates + output under ICNV_BLOCK_BYTES (default: 60 % of
+    the free device memory, at least 4 GiB — a matrix that fits stays resident and crosses PCIe once)."""
+    if "ICNV_BLOCK_BYTES" in os.environ:
+        budget = int(os.environ["ICNV_BLOCK_BYTES"])
+    else:
+        import torch
+
+        budget = max(4 << 30, int(0.6 * torch.cuda.mem_get_info()[0]))
     per_row = 4 * n_genes + 14 * n_out + 64 + (8 * n_genes + 10 * n_out if gene_values else 0)
     chunks = max(1, (budget // per_row) // chunksize)
     return min(n_rows, chunks * chunksize) if n_rows else 0

@@ -337,6 +337,36 @@ def test_layer_equals_x():
     assert (a.obsm["X_cnv"] != b.obsm["X_cnv"]).nnz == 0
 
 
+@pytest.mark.parametrize("container", ["dense", "csr"])
+def test_multi_block_equals_single_block(container, monkeypatch):
+    """A matrix that does not fit the device budget is processed in row blocks (multiples of chunksize, each block
+    uploaded for the reference pass and again for the smoothing): same result as the resident single-block path."""
+    var = cnv.datasets.synthetic_var(2400, seed=0, with_extras=True)
+    X = cnv.datasets.synthetic_counts(700, 2400, seed=21)
+    Xin = sp.csr_matrix(X) if container == "csr" else X
+    ref = X.mean(axis=0, dtype=np.float64).astype(np.float32)
+    kw = dict(chunksize=100, inplace=False, calculate_gene_values=True, reference=ref)
+    _, res1, gene1 = cnv.tl.infercnv(_adata(Xin, var), **kw)
+    small = str(300 * (4 * 2400 + 14 * res1.shape[1] + 64 + 8 * 2400 + 10 * res1.shape[1]))  # three blocks of <= 300 rows
+    monkeypatch.setenv("ICNV_BLOCK_BYTES", small)
+    _, res2, gene2 = cnv.tl.infercnv(_adata(Xin, var), **kw)
+    assert (res1 != res2).nnz == 0 and res1.shape == res2.shape  # same profile -> bit-identical
+    np.testing.assert_array_equal(np.nan_to_num(gene1, nan=-7.0), np.nan_to_num(gene2, nan=-7.0))
+    # data-derived profiles (all cells / per category) summed over several blocks: the fp64 sums are added in a
+    # different order, so the float32 profile may move by an ulp in a few columns
+    obs = pd.DataFrame({"ct": np.array(["a", "b", "c"])[np.arange(700) % 3]}, index=[str(i) for i in range(700)])
+    for extra in (dict(), dict(reference_key="ct", reference_cat=["a", "c"])):
+        kw = dict(chunksize=100, inplace=False, **extra)
+        monkeypatch.setenv("ICNV_BLOCK_BYTES", small)
+        _, res3, _ = cnv.tl.infercnv(_adata(Xin, var, obs), **kw)
+        monkeypatch.delenv("ICNV_BLOCK_BYTES")
+        _, res4, _ = cnv.tl.infercnv(_adata(Xin, var, obs), **kw)
+        a3, a4 = res3.toarray(), res4.toarray()
+        both = (a3 != 0) & (a4 != 0)
+        np.testing.assert_allclose(a3[both], a4[both], rtol=1e-5, atol=1e-7)
+        assert ((a3 != 0) != (a4 != 0)).sum() <= 3
+
+
 def test_csr_with_duplicates_and_unsorted_columns_equals_dense():
     # scipy's toarray() (_infercnv.py:423) sums duplicate entries and does not care about column order
     import scipy.sparse as sp
