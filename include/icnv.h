@@ -59,7 +59,11 @@ void icnv_plan_destroy(icnv_plan* plan);
  * tl/_infercnv.py:335-337).  out_off_host has n_seg+1 entries. */
 int icnv_plan_out_width(const icnv_plan* plan, int64_t* K);
 int icnv_plan_out_offsets(const icnv_plan* plan, int64_t* out_off_host);
-/* 0 = templated group kernel, 1 = runtime group kernel, 2 = direct-form kernel */
+/* Which smoothing kernel the plan runs (with the reference dtype installed by icnv_plan_set_reference):
+ *   0 = grouped kernel with compile-time (window, step) in {(100,10), (250,10)}; window 100 stages cell rows in pairs
+ *       when two rows fit in shared memory (dense input), one row otherwise and for CSR input;
+ *   1 = grouped kernel with runtime weights (any step that divides the window);
+ *   2 = direct-form kernel staged in parts: any (window, step), float64 centring, any gene-axis length. */
 int icnv_plan_kernel_tier(const icnv_plan* plan);
 
 /* ------------------------------------------------------- reference profile --
@@ -91,7 +95,9 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
 
 /* ------------------------------------------------------------- smoothing ----
  * Steps 1-3 of tl/_infercnv.py:411-440 for n_rows cells: centre (:422-432), clip to +-lfc_clip (:436),
- * per-chromosome pyramid running mean decimated by `step` (:179-244, :301-356).
+ * per-chromosome pyramid running mean decimated by `step` (:179-244, :301-356).  Results do not depend on which
+ * kernel tier runs, on the launch geometry or on how the rows are split into calls (bit-reproducible).
+ * icnv_smooth_csr_f32 densifies every row on load like the reference (:423); tier 2 takes dense input only.
  *   tmp   [n_rows, ld_tmp >= icnv_plan_tmp_width()] float64: the smoothed rows in the kernel's warp-tile
  *         column order (every store a full line); icnv_center_rows turns them into the natural matrix.
  */
