@@ -52,6 +52,13 @@ for window in WINDOWS:
         t_sm = timeit(lambda: plan.smooth(Xd, 3.0, tmp=tmp))
         t_ce = timeit(lambda: plan.center(tmp, out=out, row_stats=stats))
         t_th = timeit(lambda: plan.threshold(out, stats, 5000, 1.5))
+        if os.environ.get("QB_GENEVALS"):
+            thr, _, _ = plan.threshold(out, stats, 5000, 1.5)
+            ng = min(N, 10000)
+            gv = torch.empty((ng, G), dtype=torch.float64, device=dev)
+            t_gv = timeit(lambda: plan.gene_values(tmp[:ng], 5000, thr, out=gv))
+            print(json.dumps(dict(window=window, gene_values_rows=ng, gene_values_ms=t_gv, gene_values_write_GBs=ng * G * 8 / t_gv[0] / 1e6)))
+            del gv
         by = N * (4 * G + 4 * K)
         print(json.dumps(dict(window=window, N=N, K=K, launch=info,
               colsum_ms=t_cs, colsum_GBs=N*G*4/t_cs[0]/1e6,
