@@ -348,83 +348,82 @@ def infercnv(
         row_cat_host, cats = _reference_categories(adata, reference_key, reference_cat)
         n_cat = len(cats)
 
-    if True:
-        K = plan.K
-        block = _block_rows(n_rows, n_genes, K, chunksize, calculate_gene_values)
-        blocks = [(r0, min(n_rows, r0 + block)) for r0 in range(0, n_rows, max(block, 1))]
-        resident = None
-        need_sums = ref_host is None
-        sums = counts = None
-        fast_host = (
-            len(blocks) == 1
-            and isinstance(expr, np.ndarray)
-            and expr.dtype == np.float32
-            and expr.flags.c_contiguous
-            and n_rows > 0
-        )
-        if fast_host:
-            # one resident copy; the reference-profile pass rides on the transfer
-            acc = {"s": None, "c": None}
+    K = plan.K
+    block = _block_rows(n_rows, n_genes, K, chunksize, calculate_gene_values)
+    blocks = [(r0, min(n_rows, r0 + block)) for r0 in range(0, n_rows, max(block, 1))]
+    resident = None
+    need_sums = ref_host is None
+    sums = counts = None
+    fast_host = (
+        len(blocks) == 1
+        and isinstance(expr, np.ndarray)
+        and expr.dtype == np.float32
+        and expr.flags.c_contiguous
+        and n_rows > 0
+    )
+    if fast_host:
+        # one resident copy; the reference-profile pass rides on the transfer
+        acc = {"s": None, "c": None}
 
-            def on_slab(Xs, r0, r1):
-                if not need_sums:
-                    return
-                rc = torch.from_numpy(row_cat_host[r0:r1]).to(device) if row_cat_host is not None else None
-                s_, c_ = plan.colsum(Xs, rc, n_cat)
-                acc["s"] = s_ if acc["s"] is None else acc["s"].add_(s_)
-                acc["c"] = c_ if acc["c"] is None else acc["c"].add_(c_)
+        def on_slab(Xs, r0, r1):
+            if not need_sums:
+                return
+            rc = torch.from_numpy(row_cat_host[r0:r1]).to(device) if row_cat_host is not None else None
+            s_, c_ = plan.colsum(Xs, rc, n_cat)
+            acc["s"] = s_ if acc["s"] is None else acc["s"].add_(s_)
+            acc["c"] = c_ if acc["c"] is None else acc["c"].add_(c_)
 
-            resident = _upload_pipelined(expr, device, on_slab)
-            sums, counts = acc["s"], acc["c"]
-        elif len(blocks) == 1:
-            resident = _rows_to_device(expr, 0, n_rows, device)
+        resident = _upload_pipelined(expr, device, on_slab)
+        sums, counts = acc["s"], acc["c"]
+    elif len(blocks) == 1:
+        resident = _rows_to_device(expr, 0, n_rows, device)
 
-        # ---- reference profile on the device
-        if ref_host is not None:
-            c64 = np.result_type(src_dtype, ref_host.dtype) == np.float64
-            ref_dev = torch.from_numpy(np.ascontiguousarray(ref_host, dtype=np.float64 if c64 else np.float32)).to(device)
-        else:
-            row_cat_dev = None
-            if sums is None:
-                for r0, r1 in blocks:
-                    Xb = resident if resident is not None else _rows_to_device(expr, r0, r1, device)
-                    if row_cat_host is not None:
-                        row_cat_dev = torch.from_numpy(row_cat_host[r0:r1]).to(device)
-                    s, c = plan.colsum(Xb, row_cat_dev, n_cat)
-                    sums = s if sums is None else sums.add_(s)
-                    counts = c if counts is None else counts.add_(c)
-            if sums is None:  # no rows on this rank
-                sums = torch.zeros((n_cat, n_genes), dtype=torch.float64, device=device)
-                counts = torch.zeros((n_cat,), dtype=torch.int64, device=device)
-            sums, counts = allreduce_sums(sums, counts)
-            # numpy: float32 matrix -> float32 mean, anything else -> float64 (_infercnv.py:385,400)
-            ref_dev = plan.mean_from_sums(sums, counts, f64=(src_dtype != np.float32))
-        plan.set_reference(ref_dev)
+    # ---- reference profile on the device
+    if ref_host is not None:
+        c64 = np.result_type(src_dtype, ref_host.dtype) == np.float64
+        ref_dev = torch.from_numpy(np.ascontiguousarray(ref_host, dtype=np.float64 if c64 else np.float32)).to(device)
+    else:
+        row_cat_dev = None
+        if sums is None:
+            for r0, r1 in blocks:
+                Xb = resident if resident is not None else _rows_to_device(expr, r0, r1, device)
+                if row_cat_host is not None:
+                    row_cat_dev = torch.from_numpy(row_cat_host[r0:r1]).to(device)
+                s, c = plan.colsum(Xb, row_cat_dev, n_cat)
+                sums = s if sums is None else sums.add_(s)
+                counts = c if counts is None else counts.add_(c)
+        if sums is None:  # no rows on this rank
+            sums = torch.zeros((n_cat, n_genes), dtype=torch.float64, device=device)
+            counts = torch.zeros((n_cat,), dtype=torch.int64, device=device)
+        sums, counts = allreduce_sums(sums, counts)
+        # numpy: float32 matrix -> float32 mean, anything else -> float64 (_infercnv.py:385,400)
+        ref_dev = plan.mean_from_sums(sums, counts, f64=(src_dtype != np.float32))
+    plan.set_reference(ref_dev)
 
-        # ---- smoothing, noise filter, CSR (blocks are multiples of chunksize)
-        parts = []
-        # per-gene layer (_infercnv.py:141-148): dense float64 [n_obs, n_vars], NaN for genes without a value
-        per_gene = np.empty((n_rows, n_genes), dtype=np.float64) if calculate_gene_values else None
-        for r0, r1 in blocks:
-            Xb = resident if resident is not None else _rows_to_device(expr, r0, r1, device)
-            if isinstance(Xb, tuple) and plan.tier == 2:
-                Xb = _densify(Xb, n_genes, device)
-            tmp = plan.smooth(Xb, lfc_clip)
-            out, stats = plan.center(tmp)
-            thr, _, row_nnz = plan.threshold(out, stats, chunksize, dynamic_threshold)
-            if calculate_gene_values:
-                # own row median (:444), the window matrix's chunk thresholds (:453); copied out in row slabs
-                gv = plan.gene_values(tmp, chunksize, thr)
-                _to_host_into(gv, per_gene[r0:r1])
-                del gv
-            del tmp
-            indptr, indices, data = plan.to_csr(out, row_nnz)
-            parts.append(_host_csr(indptr, indices, data, (r1 - r0, K)))
-            del out, stats, Xb
-        if parts:
-            res = scipy.sparse.vstack(parts, format="csr") if len(parts) > 1 else parts[0]
-        else:
-            res = scipy.sparse.csr_matrix((0, K), dtype=np.float64)
+    # ---- smoothing, noise filter, CSR (blocks are multiples of chunksize)
+    parts = []
+    # per-gene layer (_infercnv.py:141-148): dense float64 [n_obs, n_vars], NaN for genes without a value
+    per_gene = np.empty((n_rows, n_genes), dtype=np.float64) if calculate_gene_values else None
+    for r0, r1 in blocks:
+        Xb = resident if resident is not None else _rows_to_device(expr, r0, r1, device)
+        if isinstance(Xb, tuple) and plan.tier == 2:
+            Xb = _densify(Xb, n_genes, device)
+        tmp = plan.smooth(Xb, lfc_clip)
+        out, stats = plan.center(tmp)
+        thr, _, row_nnz = plan.threshold(out, stats, chunksize, dynamic_threshold)
+        if calculate_gene_values:
+            # own row median (:444), the window matrix's chunk thresholds (:453); copied out in row slabs
+            gv = plan.gene_values(tmp, chunksize, thr)
+            _to_host_into(gv, per_gene[r0:r1])
+            del gv
+        del tmp
+        indptr, indices, data = plan.to_csr(out, row_nnz)
+        parts.append(_host_csr(indptr, indices, data, (r1 - r0, K)))
+        del out, stats, Xb
+    if parts:
+        res = scipy.sparse.vstack(parts, format="csr") if len(parts) > 1 else parts[0]
+    else:
+        res = scipy.sparse.csr_matrix((0, K), dtype=np.float64)
 
     chr_pos = layout.chr_pos
     if inplace:

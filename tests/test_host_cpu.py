@@ -139,3 +139,38 @@ def test_gather_schedule_invariants(g, sort_in_memory):
     assert cost[1] < 1.5 and cost[1] < 0.75 * cost[0]
     # too few slots -> refused
     assert lib.icnv_host_schedule_gathers(gcol.ctypes.data_as(_lib.c_i32p), n_groups, gs, n_genes, 4, 1, None, None) < 0
+
+
+def test_quantile_rule_matches_numpy_percentile():
+    """tl/_ith.py reads the quartiles of the sorted correlation entries with numpy's default ('linear') rule
+    (_scores.py:141,214 call np.percentile(pcorr, [75, 25]))."""
+    import torch
+
+    from infercnvpy_b200.tl._ith import _np_linear_quantile
+
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 5, 9, 16, 25, 1000, 4097):
+        a = np.sort(rng.normal(size=n))
+        t = torch.from_numpy(a)
+        for q in (0.25, 0.75):
+            assert _np_linear_quantile(t, n, q) == float(np.percentile(a, 100 * q)), (n, q)
+    # ties and a constant vector
+    a = np.sort(np.repeat(rng.normal(size=7), 5))
+    for q in (0.25, 0.75):
+        assert _np_linear_quantile(torch.from_numpy(a), a.size, q) == float(np.percentile(a, 100 * q))
+    ones = torch.ones(36, dtype=torch.float64)
+    assert _np_linear_quantile(ones, 36, 0.75) - _np_linear_quantile(ones, 36, 0.25) == 0.0
+
+
+def test_block_rows_are_multiples_of_chunksize(monkeypatch):
+    """Row blocks never cut a chunk (its std must see all of its rows, _infercnv.py:123,450)."""
+    from infercnvpy_b200.tl._infercnv import _block_rows
+
+    per_row = 4 * 20000 + 14 * 1792 + 64
+    monkeypatch.setenv("ICNV_BLOCK_BYTES", str(12_345 * per_row))
+    assert _block_rows(100_000, 20000, 1792, 5000) == 10_000
+    assert _block_rows(7_000, 20000, 1792, 5000) == 7_000          # everything fits: one block
+    assert _block_rows(100_000, 20000, 1792, 20_000) == 20_000     # budget below one chunk: still a whole chunk
+    assert _block_rows(0, 20000, 1792, 5000) == 0
+    # the per-gene layer needs 8*G more bytes per row
+    assert _block_rows(100_000, 20000, 1792, 1000, gene_values=True) < _block_rows(100_000, 20000, 1792, 1000)
