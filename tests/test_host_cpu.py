@@ -174,3 +174,51 @@ def test_block_rows_are_multiples_of_chunksize(monkeypatch):
     assert _block_rows(0, 20000, 1792, 5000) == 0
     # the per-gene layer needs 8*G more bytes per row
     assert _block_rows(100_000, 20000, 1792, 1000, gene_values=True) < _block_rows(100_000, 20000, 1792, 1000)
+
+
+def test_layout_matches_oracle_on_random_var_tables():
+    """Integer parity of the gene axis on adversarial var tables: ties in `start`, chromosomes that are excluded, null,
+    not `chr*`, `chrM`, names that only differ in case or need the natural sort (chr2 < chr10 < chr10_alt)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    names = ["chr1", "chr2", "chr10", "chr10_alt", "chrX", "chrY", "chrM", "chrUn_x", "scaffold7", "Chr3", "chr3", None]
+
+    @settings(max_examples=60, deadline=None)
+    @given(
+        st.integers(min_value=1, max_value=400),
+        st.integers(min_value=0, max_value=2**31 - 1),
+        st.sampled_from([(5, 1), (7, 3), (10, 10), (4, 9), (100, 10)]),
+        st.sampled_from([("chrX", "chrY"), None, ("chr1",)]),
+    )
+    def check(g, seed, ws, exclude):
+        rng = np.random.default_rng(seed)
+        window, step = ws
+        chrom = rng.choice(np.array(names, dtype=object), size=g)
+        start = rng.integers(0, max(2, g // 3), size=g)  # plenty of ties
+        var = pd.DataFrame({"chromosome": chrom, "start": start, "end": start + 10}, index=[f"g{i}" for i in range(g)])
+        lay = build_layout(var, window, step, exclude)
+        keep = ~lay.var_mask
+        chrom_s = pd.Series(chrom, dtype=object)
+        drop = chrom_s.isnull()
+        if exclude is not None:
+            drop = drop | chrom_s.isin(exclude)
+        np.testing.assert_array_equal(lay.var_mask, drop.to_numpy())
+        order = orc.natural_chromosome_order(chrom[keep])
+        assert lay.chromosomes == order
+        kept_cols = np.flatnonzero(keep)
+        widths = []
+        for i, c in enumerate(order):
+            want = kept_cols[orc.gene_order(chrom[keep], start[keep], c)]
+            np.testing.assert_array_equal(lay.gene_idx[lay.seg_off[i] : lay.seg_off[i + 1]], want)
+            g_c = want.size
+            widths.append((g_c - window) // step + 1 if window < g_c else 1)
+        np.testing.assert_array_equal(lay.out_off, np.cumsum([0] + widths))
+        if order:
+            X = rng.normal(size=(2, g)).astype(np.float32)
+            chr_pos, res = orc.infercnv(X, chrom, start, window_size=window, step=step, dynamic_threshold=None,
+                                        exclude_chromosomes=exclude, reference=np.zeros(g, np.float32))
+            assert {k: int(v) for k, v in chr_pos.items()} == {k: int(v) for k, v in lay.chr_pos.items()}
+            assert res.shape[1] == lay.n_out
+
+    check()
