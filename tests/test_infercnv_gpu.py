@@ -56,7 +56,10 @@ def _compare_thresholded(got: np.ndarray, want: np.ndarray, chunk: int, rtol=RTO
 
 
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+GPU_CASES = [c for c in CASES if c.get("gpu", True)]
+
+
+@pytest.mark.parametrize("case", GPU_CASES, ids=[c["name"] for c in GPU_CASES])
 def test_public_api_matches_reference_golden(case, golden_loader):
     """cnv.tl.infercnv with the reference's own profile == the real reference's output."""
     gold = golden_loader(case["name"])
