@@ -317,7 +317,11 @@ def main():
     tfile = ROOT / "profiles" / "smooth_traffic.json"
     if tfile.exists():
         try:
+            # measured on a launch of 100 000 cells (ncu --set full, tools/one_step.py); the kernel streams, so DRAM
+            # bytes scale with the rows of the launch
             traffic = json.load(open(tfile)).get(args.workload)
+            if traffic is not None:
+                traffic = float(traffic) * n_local / 100_000
         except Exception:
             traffic = None
     roofline = {
