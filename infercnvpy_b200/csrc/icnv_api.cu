@@ -122,6 +122,14 @@ struct icnv_plan {
     size_t parts_smem[2] = {0, 0};
 
     int rows = 1;                    // cell rows the grouped kernel stages per iteration (table layout depends on it)
+    // ---- experimental banded row-pair kernel (icnv_smooth_banded.cu; ICNV_SMOOTH_BANDS=2 at plan creation, off by default)
+    struct Banded {
+        bool on = false;
+        int32_t NG = 0, NGpad = 0;
+        int32_t units[2] = {0, 0}, tile0[2] = {0, 0}, tiles[2] = {0, 0};
+        GatherTables tab;
+        DevBuf<Task> tasks;
+    } banded;
     bool permuted = false;           // gather tables carry the element position (bits 24..27 of off_w)
     double gather_wavefronts = 0.0;  // shared-memory wavefronts per gather instruction of the schedule
 
@@ -139,6 +147,8 @@ struct icnv_plan {
     ~icnv_plan() {
         tab[0].release();
         tab[1].release();
+        banded.tab.release();
+        banded.tasks.release();
         alpha.release();
         beta.release();
         cw.release();
@@ -261,6 +271,85 @@ int build_parts(icnv_plan& p, bool c64) {
     p.n_parts[k] = (int32_t)(parts.size() / 4);
     p.parts_smem[k] = ((size_t)p.window * 8 + (size_t)(max_len + 4) * elem + 15) / 16 * 16;
     if (p.parts[k].upload(parts)) return ICNV_ECUDA;
+    return 0;
+}
+
+// Tables of the experimental banded row-pair kernel (icnv_smooth_banded.cu).  The task list is cut at a tile boundary;
+// band X keeps every group its tasks read (groups read by both bands are duplicated), band B's groups are re-based
+// behind a gap of PAD_GROUPS zero groups, every band gets its own gather schedule, band A's work units come first.
+// Leaves plan.banded.on == false when the shape does not fit (fewer than 2 or more than 8 tiles, shared memory).
+int build_banded(icnv_plan& p, const std::vector<int32_t>& gcol, const std::vector<Task>& tasks, int n_genes, uint32_t raw_base,
+                 bool optimise_walk) {
+    auto& B = p.banded;
+    const int gs = p.gs;
+    const int n_tasks = (int)tasks.size();
+    const int n_tiles = (n_tasks + 31) / 32;
+    if (n_tiles < 2 || n_tiles > 8) return 0;
+    const int TA = (n_tiles + 1) / 2;
+    const int tA = 32 * TA;  // < n_tasks because n_tiles >= 2
+    auto need_end = [&](const Task& t) { return (t.w & 0xFF) ? t.x + t.z : t.x + (t.z - 1) + p.NQ; };
+    int32_t gA_end = 0;
+    for (int t = 0; t < tA; ++t) gA_end = std::max(gA_end, need_end(tasks[t]));
+    const int32_t gB_start = tasks[tA].x;
+    const int32_t nA = gA_end, nB = p.NG - gB_start;
+    const int32_t baseB = (gA_end + PAD_GROUPS + 7) / 8 * 8;
+    B.NG = baseB + nB;
+    B.NGpad = (B.NG + 3) / 4 * 4;
+    const size_t smem = smooth_scratch_bytes() + (size_t)2 * p.Gpad * 4 + (size_t)2 * (B.NGpad + PAD_GROUPS) * 16;
+    if (smem > SMEM_MAX || p.qstar >= 0) return 0;
+    int n_wb[2];
+    std::vector<int32_t> slot[2];
+    std::vector<uint8_t> order[2];
+    const int32_t first_group[2] = {0, gB_start}, count[2] = {nA, nB}, phys0[2] = {0, baseB};
+    const int32_t dump[2] = {gA_end, B.NGpad};  // where empty slots store their zeros: the gap / the tail pad
+    for (int b = 0; b < 2; ++b) {
+        const int nquads = ((count[b] + 3) / 4 * 4) / 4;
+        n_wb[b] = std::max(1, (nquads + 31) / 32);
+        std::vector<int32_t> sub(gcol.begin() + (size_t)first_group[b] * gs, gcol.begin() + (size_t)(first_group[b] + count[b]) * gs);
+        if (schedule_gathers(sub, count[b], gs, n_genes, n_wb[b] * 4, optimise_walk, slot[b], order[b]) < 0) {
+            set_error("internal: banded group slots exhausted");
+            return ICNV_EINVAL;
+        }
+    }
+    const size_t n_entries = (size_t)(n_wb[0] + n_wb[1]) * gs * 32 * 4;
+    std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
+    std::vector<int32_t> cols(n_entries, -1);
+    std::vector<int32_t> grp((size_t)(n_wb[0] + n_wb[1]) * 32 * 4, 0);
+    for (int b = 0; b < 2; ++b)
+        for (int wb = 0; wb < n_wb[b]; ++wb) {
+            const size_t unit = (size_t)(b ? n_wb[0] : 0) + wb;
+            for (int lane = 0; lane < 32; ++lane)
+                for (int u = 0; u < 4; ++u) {
+                    const int32_t gl = slot[b][((size_t)wb * 4 + u) * 32 + lane];  // group index inside the band, -1 = none
+                    grp[(unit * 32 + lane) * 4 + u] = gl < 0 ? dump[b] : phys0[b] + gl;
+                    for (int t = 0; t < gs; ++t) {
+                        const size_t e = ((unit * gs + t) * 32 + lane) * 4 + u;
+                        int j = t;
+                        if (gl >= 0) {
+                            j = order[b][(((size_t)wb * 4 + u) * 32 + lane) * gs + t];
+                            const int32_t col = gcol[(size_t)(first_group[b] + gl) * gs + j];
+                            if (col >= 0) {
+                                off[e] = raw_base + (uint32_t)col * 4u;
+                                cols[e] = col;
+                            }
+                        }
+                        off[e] |= (uint32_t)j << 24;
+                    }
+                }
+        }
+    std::vector<Task> tb(tasks);
+    for (int t = tA; t < n_tasks; ++t) tb[t].x = baseB + (tb[t].x - gB_start);
+    B.tab.uw = 4;
+    if (B.tab.off_w.upload(off) || B.tab.cols_w.upload(cols) || B.tab.grp_w.upload(grp) || B.tab.lo_w.alloc(n_entries) ||
+        B.tab.hi_w.alloc(n_entries) || B.tasks.upload(tb))
+        return ICNV_ECUDA;
+    B.units[0] = n_wb[0];
+    B.units[1] = n_wb[1];
+    B.tile0[0] = 0;
+    B.tile0[1] = TA;
+    B.tiles[0] = TA;
+    B.tiles[1] = n_tiles - TA;
+    B.on = true;
     return 0;
 }
 
@@ -464,6 +553,13 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         if (T.off_w.upload(off) || T.cols_w.upload(cols) || T.grp_w.upload(grp) || T.lo_w.alloc(n_entries) || T.hi_w.alloc(n_entries))
             return ICNV_ECUDA;
         }  // table sets
+        {
+            const char* be = std::getenv("ICNV_SMOOTH_BANDS");
+            if (be && be[0] == '2' && pairs) {
+                const int rcb = build_banded(*p, gcol, tasks, n_genes, raw_base, optimise_walk);
+                if (rcb) return rcb;
+            }
+        }
         if (p->alpha.upload(alpha) || p->beta.upload(beta) || p->cw.upload(cw) || p->tasks_g.upload(tasks)) return ICNV_ECUDA;
     }
     if (flat_inv.empty()) flat_inv.push_back(1.0);
@@ -610,6 +706,9 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
     int rc = choose(*plan, c64, &ch);
     if (rc) return rc;
     if (ch.tier < 2) {
+        if (plan->banded.on)
+            rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->banded.tab.cols_w.ptr, (int64_t)plan->banded.tab.cols_w.n,
+                                  plan->banded.tab.lo_w.ptr, plan->banded.tab.hi_w.ptr, false, st);
         for (int ts = 0; ts < 2 && !rc; ++ts)
             if (plan->tab[ts].uw)
                 rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->tab[ts].cols_w.ptr, (int64_t)plan->tab[ts].cols_w.n,
@@ -723,6 +822,25 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
         sp.l2_prefetch = (e && e[0] == '0') ? 0 : 1;
         const char* e2 = std::getenv("ICNV_SPLIT_ROWS");
         sp.split_rows = (e2 && e2[0] == '0') ? 0 : 1;
+    }
+    if (plan->banded.on && ch.tier == 0 && ch.rows == 2 && sp.use_tma) {
+        // experimental banded kernel (off unless ICNV_SMOOTH_BANDS=2 was set when the plan was created)
+        const auto& B = plan->banded;
+        sp.NG = B.NG;
+        sp.NGpad = B.NGpad;
+        sp.off_w = B.tab.off_w.ptr;
+        sp.grp_w = B.tab.grp_w.ptr;
+        sp.lo_w = B.tab.lo_w.ptr;
+        sp.hi_w = B.tab.hi_w.ptr;
+        sp.tasks = B.tasks.ptr;
+        for (int b = 0; b < 2; ++b) {
+            sp.band_units[b] = B.units[b];
+            sp.band_tile0[b] = B.tile0[b];
+            sp.band_tiles[b] = B.tiles[b];
+        }
+        const size_t smem_b = smooth_scratch_bytes() + (size_t)2 * plan->Gpad * 4 + (size_t)2 * (B.NGpad + PAD_GROUPS) * 16;
+        const int grid_b = (int)std::min<int64_t>((sp.n_rows + 1) / 2, (int64_t)plan->n_sm);
+        return smooth_banded_launch(plan->bounded, sp, grid_b, (smem_b + 15) / 16 * 16, (cudaStream_t)stream);
     }
     int occ = 0;
     rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);

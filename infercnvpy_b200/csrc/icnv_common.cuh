@@ -82,6 +82,10 @@ struct SmoothParams {
     // optional developer timeline: [grid][dbg_rows][16] clock64 stamps (nullptr = off)
     long long* dbg;
     int32_t dbg_rows;
+    // ---- experimental banded kernel only (icnv_smooth_banded.cu): units / tiles of band A and band B
+    int32_t band_units[2];
+    int32_t band_tile0[2];
+    int32_t band_tiles[2];
 };
 
 // general direct-form smoothing (icnv_direct.cu)
@@ -214,6 +218,7 @@ int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, i
                   size_t smem, cudaStream_t stream);
 int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm);
 
+int smooth_banded_launch(bool bounded, const SmoothParams& p, int grid, size_t smem, cudaStream_t stream);
 int direct_launch(const DirectParams& p, bool bounded, bool c64, int grid, size_t smem, cudaStream_t st);
 int center_wide_launch(const double* tmp, int64_t n_rows, int64_t ld, const int32_t* kaddr, int K, void* out, bool f64, int64_t ldo,
                        double* row_stats, int n_sm, cudaStream_t st);
