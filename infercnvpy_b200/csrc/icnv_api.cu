@@ -274,81 +274,32 @@ int build_parts(icnv_plan& p, bool c64) {
     return 0;
 }
 
-// Tables of the experimental banded row-pair kernel (icnv_smooth_banded.cu).  The task list is cut at a tile boundary;
-// band X keeps every group its tasks read (groups read by both bands are duplicated), band B's groups are re-based
-// behind a gap of PAD_GROUPS zero groups, every band gets its own gather schedule, band A's work units come first.
-// Leaves plan.banded.on == false when the shape does not fit (fewer than 2 or more than 8 tiles, shared memory).
+// Tables of the experimental banded row-pair kernel: the layout itself is host-only code (icnv_banded_host.cu, also
+// reachable from the CPU tests); here it is checked against shared memory and uploaded.
 int build_banded(icnv_plan& p, const std::vector<int32_t>& gcol, const std::vector<Task>& tasks, int n_genes, uint32_t raw_base,
                  bool optimise_walk) {
     auto& B = p.banded;
-    const int gs = p.gs;
-    const int n_tasks = (int)tasks.size();
-    const int n_tiles = (n_tasks + 31) / 32;
-    if (n_tiles < 2 || n_tiles > 8) return 0;
-    const int TA = (n_tiles + 1) / 2;
-    const int tA = 32 * TA;  // < n_tasks because n_tiles >= 2
-    auto need_end = [&](const Task& t) { return (t.w & 0xFF) ? t.x + t.z : t.x + (t.z - 1) + p.NQ; };
-    int32_t gA_end = 0;
-    for (int t = 0; t < tA; ++t) gA_end = std::max(gA_end, need_end(tasks[t]));
-    const int32_t gB_start = tasks[tA].x;
-    const int32_t nA = gA_end, nB = p.NG - gB_start;
-    const int32_t baseB = (gA_end + PAD_GROUPS + 7) / 8 * 8;
-    B.NG = baseB + nB;
-    B.NGpad = (B.NG + 3) / 4 * 4;
-    const size_t smem = smooth_scratch_bytes() + (size_t)2 * p.Gpad * 4 + (size_t)2 * (B.NGpad + PAD_GROUPS) * 16;
-    if (smem > SMEM_MAX || p.qstar >= 0) return 0;
-    int n_wb[2];
-    std::vector<int32_t> slot[2];
-    std::vector<uint8_t> order[2];
-    const int32_t first_group[2] = {0, gB_start}, count[2] = {nA, nB}, phys0[2] = {0, baseB};
-    const int32_t dump[2] = {gA_end, B.NGpad};  // where empty slots store their zeros: the gap / the tail pad
-    for (int b = 0; b < 2; ++b) {
-        const int nquads = ((count[b] + 3) / 4 * 4) / 4;
-        n_wb[b] = std::max(1, (nquads + 31) / 32);
-        std::vector<int32_t> sub(gcol.begin() + (size_t)first_group[b] * gs, gcol.begin() + (size_t)(first_group[b] + count[b]) * gs);
-        if (schedule_gathers(sub, count[b], gs, n_genes, n_wb[b] * 4, optimise_walk, slot[b], order[b]) < 0) {
-            set_error("internal: banded group slots exhausted");
-            return ICNV_EINVAL;
-        }
+    if (p.qstar >= 0) return 0;
+    BandedLayout L;
+    const int rc = banded_layout(gcol, p.NG, p.gs, p.NQ, tasks, n_genes, raw_base, optimise_walk, L);
+    if (rc < 0) {
+        set_error("internal: banded group slots exhausted");
+        return ICNV_EINVAL;
     }
-    const size_t n_entries = (size_t)(n_wb[0] + n_wb[1]) * gs * 32 * 4;
-    std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
-    std::vector<int32_t> cols(n_entries, -1);
-    std::vector<int32_t> grp((size_t)(n_wb[0] + n_wb[1]) * 32 * 4, 0);
-    for (int b = 0; b < 2; ++b)
-        for (int wb = 0; wb < n_wb[b]; ++wb) {
-            const size_t unit = (size_t)(b ? n_wb[0] : 0) + wb;
-            for (int lane = 0; lane < 32; ++lane)
-                for (int u = 0; u < 4; ++u) {
-                    const int32_t gl = slot[b][((size_t)wb * 4 + u) * 32 + lane];  // group index inside the band, -1 = none
-                    grp[(unit * 32 + lane) * 4 + u] = gl < 0 ? dump[b] : phys0[b] + gl;
-                    for (int t = 0; t < gs; ++t) {
-                        const size_t e = ((unit * gs + t) * 32 + lane) * 4 + u;
-                        int j = t;
-                        if (gl >= 0) {
-                            j = order[b][(((size_t)wb * 4 + u) * 32 + lane) * gs + t];
-                            const int32_t col = gcol[(size_t)(first_group[b] + gl) * gs + j];
-                            if (col >= 0) {
-                                off[e] = raw_base + (uint32_t)col * 4u;
-                                cols[e] = col;
-                            }
-                        }
-                        off[e] |= (uint32_t)j << 24;
-                    }
-                }
-        }
-    std::vector<Task> tb(tasks);
-    for (int t = tA; t < n_tasks; ++t) tb[t].x = baseB + (tb[t].x - gB_start);
+    if (!L.on) return 0;
+    const size_t smem = smooth_scratch_bytes() + (size_t)2 * p.Gpad * 4 + (size_t)2 * (L.NGpad + PAD_GROUPS) * 16;
+    if (smem > SMEM_MAX) return 0;
+    B.NG = L.NG;
+    B.NGpad = L.NGpad;
     B.tab.uw = 4;
-    if (B.tab.off_w.upload(off) || B.tab.cols_w.upload(cols) || B.tab.grp_w.upload(grp) || B.tab.lo_w.alloc(n_entries) ||
-        B.tab.hi_w.alloc(n_entries) || B.tasks.upload(tb))
+    if (B.tab.off_w.upload(L.off) || B.tab.cols_w.upload(L.cols) || B.tab.grp_w.upload(L.grp) || B.tab.lo_w.alloc(L.off.size()) ||
+        B.tab.hi_w.alloc(L.off.size()) || B.tasks.upload(L.tasks))
         return ICNV_ECUDA;
-    B.units[0] = n_wb[0];
-    B.units[1] = n_wb[1];
-    B.tile0[0] = 0;
-    B.tile0[1] = TA;
-    B.tiles[0] = TA;
-    B.tiles[1] = n_tiles - TA;
+    for (int b = 0; b < 2; ++b) {
+        B.units[b] = L.units[b];
+        B.tile0[b] = L.tile0[b];
+        B.tiles[b] = L.tiles[b];
+    }
     B.on = true;
     return 0;
 }
