@@ -70,14 +70,12 @@ CASES = [
     # bench-shaped gene axis
     dict(name="gv_g20k", n=8, g=20000, extras=False, seed=2005, gene_values=True, kw=dict(chunksize=5)),
     # ---- shapes of the reference's two tutorial notebooks, synthetic stand-ins ----
-    # These pin the ORACLE at those shapes.  `gpu=False`: the CUDA parity tests skip them until the combination
-    # "bounded centring on the direct kernel staged in parts" has been run on a B200 (it was written after the last
-    # GPU session of round 1; enable by deleting the flag).
+    # (bounded centring on the direct kernel staged in parts / wide-row median)
     # tutorial_3k: ~58k genes, window 250, step 10, several reference categories -> ~5300 columns
-    dict(name="tutorial_3k_like", n=16, g=58000, extras=True, seed=3001, obs_cats=4, gpu=False,
+    dict(name="tutorial_3k_like", n=16, g=58000, extras=True, seed=3001, obs_cats=4,
          kw=dict(window_size=250, chunksize=5000, reference_key="cell_type", reference_cat=["c0", "c1", "c3"])),
     # reproduce_infercnv: ~11k genes, window 100, step 1, two reference categories -> ~9000 columns
-    dict(name="reproduce_like", n=12, g=11000, extras=False, seed=3002, obs_cats=3, gpu=False,
+    dict(name="reproduce_like", n=12, g=11000, extras=False, seed=3002, obs_cats=3,
          kw=dict(window_size=100, step=1, chunksize=5000, reference_key="cell_type", reference_cat=["c0", "c2"])),
 ]
 
