@@ -206,15 +206,6 @@ int icnv_plan_gather_cost(const icnv_plan* plan, double* wavefronts_per_gather);
 double icnv_host_schedule_gathers(const int32_t* gcol, int32_t n_groups, int32_t gs, int32_t n_genes, int32_t nsets,
                                   int32_t permute, int32_t* slot_group_out, uint8_t* order_out);
 
-/* Host-only (no device needed): table layout of the EXPERIMENTAL banded row-pair kernel (csrc/icnv_banded_host.cu; the
- * kernel is off by default and not part of the product path) on caller-supplied groups gcol [n_groups, gs] and tasks
- * tasks4 [n_tasks, 4] (x = first group, y = first output column, z = outputs or groups, w = kind | flat index << 8).
- * meta_out [9] = {on, NG, NGpad, units A, units B, first tile of B, tiles A, tiles B, table entries}.  Used by the CPU
- * tests, which emulate the kernel's data flow in numpy from these tables. */
-int icnv_host_banded_layout(const int32_t* gcol, int32_t n_groups, int32_t gs, int32_t nq, const int32_t* tasks4,
-                            int32_t n_tasks, int32_t n_genes, uint32_t raw_base, int32_t* meta_out, uint32_t* off_out,
-                            int32_t* cols_out, int64_t cap_entries, int32_t* grp_out, int64_t cap_grp, int32_t* tasks4_out);
-
 /* Developer aid (tools/timeline.py): when dev_buf != NULL the smoothing kernel writes clock64 stamps
  * [grid][rows_per_cta][16] for the first rows_per_cta rows of every CTA.  NULL switches it off. */
 int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta);

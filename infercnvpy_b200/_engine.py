@@ -276,6 +276,55 @@ def allreduce_sums(sums, counts):
     return s.to(sums.device), c.to(counts.device)
 
 
+def _dist_world():
+    """(initialised, world size) of the default torch.distributed group."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return True, dist.get_world_size()
+    return False, 1
+
+
+def allreduce_host_counts(vec: np.ndarray) -> np.ndarray:
+    """Sum a small host int64 vector over all ranks (host-side validation that every rank has to agree on:
+    a rank raising alone would leave the others hanging in the next collective).  Identity without a group."""
+    import torch
+    import torch.distributed as dist
+
+    on, world = _dist_world()
+    v = np.ascontiguousarray(vec, dtype=np.int64)
+    if not on or world == 1:
+        return v
+    t = torch.from_numpy(v.copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+    dist.all_reduce(t)
+    return t.numpy()
+
+
+def global_label_order(local_labels) -> list:
+    """Deterministic label list shared by every rank: labels in order of first appearance over the ranks' shards taken
+    in rank order, i.e. ``pd.unique`` of the concatenated column when shards are contiguous row blocks — the key order
+    of the reference's result dict (tl/_scores.py:65-68).  Without a group: the local order."""
+    import torch.distributed as dist
+
+    local = list(local_labels)
+    on, world = _dist_world()
+    if not on or world == 1:
+        return local
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    seen, order = set(), []
+    for part in gathered:
+        for lab in part:
+            if lab not in seen:
+                seen.add(lab)
+                order.append(lab)
+    return order
+
+
 def label_scores(lib, row_abs, labels_dev, n_labels: int, K: int, device):
     """Per-label ``sum|x| / (rows * K)`` with the cross-rank reduction (tl/_scores.py:65-68)."""
     import torch

@@ -52,8 +52,6 @@ SIGNATURES = {
     "icnv_weighted_degree": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
     "icnv_louvain_sweep": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, C.c_double, C.c_int32, c_vp, c_vp, c_vp]),
     "icnv_host_schedule_gathers": (C.c_double, [c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.POINTER(C.c_uint8)]),
-    "icnv_host_banded_layout": (C.c_int, [c_i32p, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.c_int32, C.c_int32, C.c_uint32, c_i32p,
-                                          C.POINTER(C.c_uint32), c_i32p, C.c_int64, c_i32p, C.c_int64, c_i32p]),
     "icnv_debug_set_timeline": (C.c_int, [c_vp, C.c_int]),
     "icnv_label_sums": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int32, c_vp, c_vp, c_vp]),
 }

@@ -122,14 +122,6 @@ struct icnv_plan {
     size_t parts_smem[2] = {0, 0};
 
     int rows = 1;                    // cell rows the grouped kernel stages per iteration (table layout depends on it)
-    // ---- experimental banded row-pair kernel (icnv_smooth_banded.cu; ICNV_SMOOTH_BANDS=2 at plan creation, off by default)
-    struct Banded {
-        bool on = false;
-        int32_t NG = 0, NGpad = 0;
-        int32_t units[2] = {0, 0}, tile0[2] = {0, 0}, tiles[2] = {0, 0};
-        GatherTables tab;
-        DevBuf<Task> tasks;
-    } banded;
     bool permuted = false;           // gather tables carry the element position (bits 24..27 of off_w)
     double gather_wavefronts = 0.0;  // shared-memory wavefronts per gather instruction of the schedule
 
@@ -147,8 +139,6 @@ struct icnv_plan {
     ~icnv_plan() {
         tab[0].release();
         tab[1].release();
-        banded.tab.release();
-        banded.tasks.release();
         alpha.release();
         beta.release();
         cw.release();
@@ -271,36 +261,6 @@ int build_parts(icnv_plan& p, bool c64) {
     p.n_parts[k] = (int32_t)(parts.size() / 4);
     p.parts_smem[k] = ((size_t)p.window * 8 + (size_t)(max_len + 4) * elem + 15) / 16 * 16;
     if (p.parts[k].upload(parts)) return ICNV_ECUDA;
-    return 0;
-}
-
-// Tables of the experimental banded row-pair kernel: the layout itself is host-only code (icnv_banded_host.cu, also
-// reachable from the CPU tests); here it is checked against shared memory and uploaded.
-int build_banded(icnv_plan& p, const std::vector<int32_t>& gcol, const std::vector<Task>& tasks, int n_genes, uint32_t raw_base,
-                 bool optimise_walk) {
-    auto& B = p.banded;
-    if (p.qstar >= 0) return 0;
-    BandedLayout L;
-    const int rc = banded_layout(gcol, p.NG, p.gs, p.NQ, tasks, n_genes, raw_base, optimise_walk, L);
-    if (rc < 0) {
-        set_error("internal: banded group slots exhausted");
-        return ICNV_EINVAL;
-    }
-    if (!L.on) return 0;
-    const size_t smem = smooth_scratch_bytes() + (size_t)2 * p.Gpad * 4 + (size_t)2 * (L.NGpad + PAD_GROUPS) * 16;
-    if (smem > SMEM_MAX) return 0;
-    B.NG = L.NG;
-    B.NGpad = L.NGpad;
-    B.tab.uw = 4;
-    if (B.tab.off_w.upload(L.off) || B.tab.cols_w.upload(L.cols) || B.tab.grp_w.upload(L.grp) || B.tab.lo_w.alloc(L.off.size()) ||
-        B.tab.hi_w.alloc(L.off.size()) || B.tasks.upload(L.tasks))
-        return ICNV_ECUDA;
-    for (int b = 0; b < 2; ++b) {
-        B.units[b] = L.units[b];
-        B.tile0[b] = L.tile0[b];
-        B.tiles[b] = L.tiles[b];
-    }
-    B.on = true;
     return 0;
 }
 
@@ -504,13 +464,6 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         if (T.off_w.upload(off) || T.cols_w.upload(cols) || T.grp_w.upload(grp) || T.lo_w.alloc(n_entries) || T.hi_w.alloc(n_entries))
             return ICNV_ECUDA;
         }  // table sets
-        {
-            const char* be = std::getenv("ICNV_SMOOTH_BANDS");
-            if (be && be[0] == '2' && pairs) {
-                const int rcb = build_banded(*p, gcol, tasks, n_genes, raw_base, optimise_walk);
-                if (rcb) return rcb;
-            }
-        }
         if (p->alpha.upload(alpha) || p->beta.upload(beta) || p->cw.upload(cw) || p->tasks_g.upload(tasks)) return ICNV_ECUDA;
     }
     if (flat_inv.empty()) flat_inv.push_back(1.0);
@@ -657,9 +610,6 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
     int rc = choose(*plan, c64, &ch);
     if (rc) return rc;
     if (ch.tier < 2) {
-        if (plan->banded.on)
-            rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->banded.tab.cols_w.ptr, (int64_t)plan->banded.tab.cols_w.n,
-                                  plan->banded.tab.lo_w.ptr, plan->banded.tab.hi_w.ptr, false, st);
         for (int ts = 0; ts < 2 && !rc; ++ts)
             if (plan->tab[ts].uw)
                 rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->tab[ts].cols_w.ptr, (int64_t)plan->tab[ts].cols_w.n,
@@ -773,25 +723,6 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
         sp.l2_prefetch = (e && e[0] == '0') ? 0 : 1;
         const char* e2 = std::getenv("ICNV_SPLIT_ROWS");
         sp.split_rows = (e2 && e2[0] == '0') ? 0 : 1;
-    }
-    if (plan->banded.on && ch.tier == 0 && ch.rows == 2 && sp.use_tma) {
-        // experimental banded kernel (off unless ICNV_SMOOTH_BANDS=2 was set when the plan was created)
-        const auto& B = plan->banded;
-        sp.NG = B.NG;
-        sp.NGpad = B.NGpad;
-        sp.off_w = B.tab.off_w.ptr;
-        sp.grp_w = B.tab.grp_w.ptr;
-        sp.lo_w = B.tab.lo_w.ptr;
-        sp.hi_w = B.tab.hi_w.ptr;
-        sp.tasks = B.tasks.ptr;
-        for (int b = 0; b < 2; ++b) {
-            sp.band_units[b] = B.units[b];
-            sp.band_tile0[b] = B.tile0[b];
-            sp.band_tiles[b] = B.tiles[b];
-        }
-        const size_t smem_b = smooth_scratch_bytes() + (size_t)2 * plan->Gpad * 4 + (size_t)2 * (B.NGpad + PAD_GROUPS) * 16;
-        const int grid_b = (int)std::min<int64_t>((sp.n_rows + 1) / 2, (int64_t)plan->n_sm);
-        return smooth_banded_launch(plan->bounded, sp, grid_b, (smem_b + 15) / 16 * 16, (cudaStream_t)stream);
     }
     int occ = 0;
     rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);

@@ -82,10 +82,6 @@ struct SmoothParams {
     // optional developer timeline: [grid][dbg_rows][16] clock64 stamps (nullptr = off)
     long long* dbg;
     int32_t dbg_rows;
-    // ---- experimental banded kernel only (icnv_smooth_banded.cu): units / tiles of band A and band B
-    int32_t band_units[2];
-    int32_t band_tile0[2];
-    int32_t band_tiles[2];
 };
 
 // general direct-form smoothing (icnv_direct.cu)
@@ -218,22 +214,9 @@ int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, i
                   size_t smem, cudaStream_t stream);
 int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm);
 
-int smooth_banded_launch(bool bounded, const SmoothParams& p, int grid, size_t smem, cudaStream_t stream);
 int direct_launch(const DirectParams& p, bool bounded, bool c64, int grid, size_t smem, cudaStream_t st);
 int center_wide_launch(const double* tmp, int64_t n_rows, int64_t ld, const int32_t* kaddr, int K, void* out, bool f64, int64_t ldo,
                        double* row_stats, int n_sm, cudaStream_t st);
-// icnv_banded_host.cu (host only): layout of the experimental banded kernel's tables
-struct BandedLayout {
-    bool on = false;                 // false: the shape does not fit (fewer than 2 / more than 8 task tiles)
-    int32_t NG = 0, NGpad = 0;       // physical groups (band A, gap, band B) and their padded count
-    int32_t units[2] = {0, 0}, tile0[2] = {0, 0}, tiles[2] = {0, 0};
-    std::vector<uint32_t> off;       // [unit][step][lane][4] shared-window address | element position << 24
-    std::vector<int32_t> cols;       // same layout, matrix column (-1 = pad)
-    std::vector<int32_t> grp;        // [unit][lane][4] physical group the slot's partial sums go to
-    std::vector<Task> tasks;         // task list with band B's first group re-based
-};
-int banded_layout(const std::vector<int32_t>& gcol, int NG, int gs, int NQ, const std::vector<Task>& tasks, int n_genes,
-                  uint32_t raw_base, bool optimise_walk, BandedLayout& out);
 // icnv_schedule.cu (host only)
 double schedule_gathers(const std::vector<int32_t>& gcol, int NG, int gs, int n_genes, int nsets, bool permute,
                         std::vector<int32_t>& slot_group, std::vector<uint8_t>& order);

@@ -13,7 +13,7 @@ import numpy as np
 import scipy.sparse
 
 from .. import _lib
-from .._engine import DevicePlan, allreduce_sums
+from .._engine import DevicePlan, allreduce_host_counts, allreduce_sums
 from .._layout import build_layout
 
 log = logging.getLogger("infercnvpy_b200")
@@ -238,7 +238,7 @@ def _cached_plan(var, window_size, step, exclude_chromosomes, device):
     import hashlib
 
     h = hashlib.sha1()
-    h.update(np.asarray(var["chromosome"].astype(str)).astype("S").tobytes())
+    h.update("\x00".join(map(str, var["chromosome"].astype(str))).encode("utf-8"))
     h.update(np.ascontiguousarray(np.asarray(var["start"], dtype=np.float64)).tobytes())
     key = (h.hexdigest(), int(window_size), int(step), None if exclude_chromosomes is None else tuple(exclude_chromosomes), str(device))
     hit = _PLAN_CACHE.get(key)
@@ -246,31 +246,36 @@ def _cached_plan(var, window_size, step, exclude_chromosomes, device):
         layout = build_layout(var, window_size, step, exclude_chromosomes)
         hit = (layout, DevicePlan(layout, device))
         if len(_PLAN_CACHE) >= 4:
-            _, old = _PLAN_CACHE.popitem()
+            old = _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))  # oldest entry first
             old[1].close()
         _PLAN_CACHE[key] = hit
     return hit
 
 
 def _reference_categories(adata, reference_key, reference_cat):
-    """-> (row_cat int32 [n] with -1 for non-reference cells, n_cat).  _infercnv.py:388-398."""
+    """-> (row_cat int32 [n] with -1 for non-reference cells, categories).  _infercnv.py:388-398.
+
+    A category listed twice gives two identical reference rows in the reference, i.e. the same bounds as listing it
+    once: duplicates are dropped.  Under an initialised ``torch.distributed`` group the "not found" check runs on the
+    cell counts summed over all ranks (a shard without any cell of a rare category is fine) and raises on every rank."""
     obs_col = adata.obs[reference_key]
     if isinstance(reference_cat, str):
         reference_cat = [reference_cat]
-    reference_cat = np.array(reference_cat)
-    present = np.isin(reference_cat, obs_col)
+    reference_cat = np.array(list(dict.fromkeys(reference_cat)))
+    values = np.asarray(obs_col.values)
+    row_cat = np.full(values.shape[0], -1, dtype=np.int32)
+    local = np.zeros(len(reference_cat), dtype=np.int64)
+    for i, cat in enumerate(reference_cat):
+        m = values == cat
+        row_cat[m] = i
+        local[i] = int(np.count_nonzero(m))
+    present = allreduce_host_counts(local) > 0
     if not np.all(present):
         raise ValueError(
             "The following reference categories were not found in "
             "adata.obs[reference_key]: "
             f"{reference_cat[~present]}"
         )
-    values = np.asarray(obs_col.values)
-    row_cat = np.full(values.shape[0], -1, dtype=np.int32)
-    # later categories win like the reference's vstack of independent masks would not care: a cell
-    # has one value, so masks are disjoint unless a category is listed twice
-    for i, cat in enumerate(reference_cat):
-        row_cat[values == cat] = i
     return row_cat, reference_cat
 
 

@@ -11,7 +11,7 @@ import pandas as pd
 import scipy.sparse as sp
 
 from .. import _lib
-from .._engine import label_scores
+from .._engine import global_label_order, label_scores
 
 
 def cnv_score(
@@ -27,7 +27,8 @@ def cnv_score(
 
     Same parameters / return as the reference (``_scores.py:14-74``): per group
     ``mean(abs(X_cnv[group rows, :]))`` over ALL entries (zeros included, ``:66``).  Under an
-    initialised ``torch.distributed`` group the per-group sums are reduced over all ranks.
+    initialised ``torch.distributed`` group every rank passes its row shard; the label list is the union over ranks
+    (order of first appearance in rank order) and the per-group sums / row counts are reduced over all ranks.
     """
     import torch
 
@@ -45,7 +46,8 @@ def cnv_score(
 
     X = adata.obsm[f"X_{use_rep}"]
     groups = adata.obs[groupby]
-    clusters = list(pd.unique(groups))
+    # sharded call: every rank must index the same label list (a rank-local pd.unique would misalign the all-reduce)
+    clusters = global_label_order(pd.unique(groups))
     codes = pd.Categorical(groups, categories=clusters).codes.astype(np.int32)
     n, K = X.shape
 

@@ -70,3 +70,42 @@ def test_single_process_is_identity():
     s, c = torch.ones(2, 3, dtype=torch.float64), torch.ones(2, dtype=torch.int64)
     s2, c2 = allreduce_sums(s, c)
     assert s2 is s and c2 is c
+
+
+def _label_worker(rank, world, port, out_dir):
+    """Host logic of the sharded cnv_score / reference-category validation: shards that see different,
+    reordered or missing groups must agree on one label list, and a category missing on ONE rank is not an error."""
+    import pandas as pd
+
+    from infercnvpy_b200 import AnnData
+    from infercnvpy_b200._engine import allreduce_host_counts, global_label_order
+    from infercnvpy_b200.tl._infercnv import _reference_categories
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = [["b", "a", "b", "c"], ["c", "d", "a"]]  # rank 1 never sees "b", sees "c" first
+        order = global_label_order(pd.unique(pd.Series(shards[rank])))
+        assert order == ["b", "a", "c", "d"] == list(pd.unique(pd.Series(shards[0] + shards[1])))
+        # per-label sums indexed by the global list line up across ranks
+        codes = pd.Categorical(shards[rank], categories=order).codes
+        local = np.bincount(codes, minlength=len(order)).astype(np.int64)
+        total = allreduce_host_counts(local)
+        np.testing.assert_array_equal(total, [2, 2, 2, 1])
+        # reference categories: "T" only lives on rank 0 -> fine on both ranks; "zzz" nowhere -> ValueError on BOTH
+        obs = pd.DataFrame({"ct": (["T", "x", "x"] if rank == 0 else ["x", "y", "x"])}, index=[f"c{i}" for i in range(3)])
+        ad = AnnData(np.zeros((3, 4), dtype=np.float32), obs=obs)
+        row_cat, cats = _reference_categories(ad, "ct", ["T", "y", "T"])
+        assert list(cats) == ["T", "y"]  # the duplicate is dropped
+        np.testing.assert_array_equal(row_cat, [0, -1, -1] if rank == 0 else [-1, 1, -1])
+        with pytest.raises(ValueError, match="reference categories were not found"):
+            _reference_categories(ad, "ct", ["T", "zzz"])
+        open(os.path.join(out_dir, f"ok_{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_label_order_and_category_validation_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_label_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()

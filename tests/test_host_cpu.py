@@ -224,96 +224,3 @@ def test_layout_matches_oracle_on_random_var_tables():
     check()
 
 
-@pytest.mark.parametrize("g,window,step", [(20000, 100, 10), (9000, 100, 10)])
-def test_banded_layout_reproduces_the_oracle_smoothing(g, window, step):
-    """EXPERIMENTAL banded kernel (csrc/icnv_smooth_banded.cu, off by default): its table layout is host-only code
-    (csrc/icnv_banded_host.cu).  Here the kernel's data flow is emulated in numpy FROM THOSE TABLES — gathers through
-    (address, element position) entries into per-group partial sums A = sum x, B = sum j*x at the physical group
-    indices, then the window formula per task — and compared with the oracle's smoothing.  Also checks that the two
-    bands touch disjoint ranges of the partial-sum array (what lets their phases overlap)."""
-    lib = _lib.load()
-    var = cnv.datasets.synthetic_var(g, seed=0)
-    lay = build_layout(var, window, step)
-    gcol, n_genes = _group_table(var, window, step)
-    n_groups, gs = gcol.shape
-    nq = window // step
-    # task list like icnv_plan_create: up to 9 consecutive outputs per task, one task per flat chromosome
-    tasks, flat_genes, gbase = [], [], 0
-    for ci in range(len(lay.chromosomes)):
-        g_c = int(lay.seg_off[ci + 1] - lay.seg_off[ci])
-        out0 = int(lay.out_off[ci])
-        if window < g_c:
-            n_out = (g_c - window) // step + 1
-            for k in range(0, n_out, 9):
-                tasks.append((gbase + k, out0 + k, min(9, n_out - k), 0))
-            gbase += n_out - 1 + nq
-        else:
-            n_grp = -(-g_c // step)
-            tasks.append((gbase, out0, n_grp, 1 | (len(flat_genes) << 8)))
-            flat_genes.append(g_c)
-            gbase += n_grp
-    assert gbase == n_groups
-    tasks = np.asarray(tasks, dtype=np.int32)
-    raw_base = 0x420
-    meta = np.zeros(9, dtype=np.int32)
-    cap_e, cap_g = (n_groups // 128 + 4) * gs * 128, (n_groups // 128 + 4) * 128
-    off = np.zeros(cap_e, dtype=np.uint32)
-    cols = np.zeros(cap_e, dtype=np.int32)
-    grp = np.zeros(cap_g, dtype=np.int32)
-    tasks_b = np.zeros_like(tasks)
-    rc = lib.icnv_host_banded_layout(
-        gcol.ctypes.data_as(_lib.c_i32p), n_groups, gs, nq, tasks.ctypes.data_as(_lib.c_i32p), len(tasks), n_genes, raw_base,
-        meta.ctypes.data_as(_lib.c_i32p), off.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), cols.ctypes.data_as(_lib.c_i32p),
-        cap_e, grp.ctypes.data_as(_lib.c_i32p), cap_g, tasks_b.ctypes.data_as(_lib.c_i32p),
-    )
-    assert rc == 0
-    on, NG, NGpad, units_a, units_b, tile0_b, tiles_a, tiles_b, n_entries = (int(v) for v in meta)
-    n_tiles = -(-len(tasks) // 32)
-    assert on == 1 and tiles_a + tiles_b == n_tiles and tile0_b == tiles_a and max(tiles_a, tiles_b) <= 4
-    n_units = units_a + units_b
-    assert n_entries == n_units * gs * 128
-    off, cols = off[:n_entries].reshape(n_units, gs, 32, 4), cols[:n_entries].reshape(n_units, gs, 32, 4)
-    grp = grp[: n_units * 128].reshape(n_units, 32, 4)
-    # entries: address of the gene (or of the zero pad slot) + element position in bits 24..27
-    addr, pos = off & 0xFFFFFF, off >> 24
-    np.testing.assert_array_equal(addr, raw_base + 4 * np.where(cols < 0, n_genes, cols))
-    assert pos.max() < gs
-    # the bands own disjoint ranges of the partial-sum array, separated by >= 12 untouched groups
-    a_hi = grp[:units_a].max()
-    b_lo = grp[units_a:].min()
-    real_a = sorted(set(grp[:units_a].ravel().tolist()))
-    assert b_lo - (real_a[-2] if len(real_a) > 1 else a_hi) > 12 and b_lo % 8 == 0 and grp.max() <= NGpad
-    real_slot = (cols >= 0).any(axis=1)  # [unit, lane, u]: the slot holds a group with at least one real gene
-    lanes = np.broadcast_to(np.arange(32)[None, :, None], grp.shape)
-    assert np.all(grp[real_slot] % 8 == lanes[real_slot] % 8)  # a quarter-warp's partial-sum stores hit 8 bank groups
-    tA = 32 * tiles_a
-    np.testing.assert_array_equal(tasks_b[:tA], tasks[:tA])
-    np.testing.assert_array_equal(tasks_b[tA:, 1:], tasks[tA:, 1:])
-    assert tasks_b[tA, 0] == b_lo
-    # ---- emulate the kernel on two cell rows
-    rng = np.random.default_rng(5)
-    X = cnv.datasets.synthetic_counts(2, g, seed=17)
-    ref = rng.uniform(0.0, 0.5, size=g).astype(np.float32)
-    d = np.clip(X - ref, -3, 3).astype(np.float32)
-    dpad = np.concatenate([d, np.zeros((2, 1), np.float32)], axis=1).astype(np.float64)  # slot n_genes = zero pad
-    AB = np.zeros((2, NGpad + 12, 2))
-    src = np.where(cols < 0, n_genes, cols)
-    for u in range(n_units):
-        vals = dpad[:, src[u]]                               # [2, gs, 32, 4]
-        a = vals.sum(axis=1)
-        b = (vals * pos[u][None].astype(np.float64)).sum(axis=1)
-        AB[:, grp[u].ravel(), 0] = a.reshape(2, -1)
-        AB[:, grp[u].ravel(), 1] = b.reshape(2, -1)
-    w0 = np.array([min(10 * q + 1, window - 10 * q) for q in range(nq)], dtype=np.float64)            # weight of j = 0
-    w1 = np.array([min(10 * q + 2, window - 10 * q - 1) for q in range(nq)], dtype=np.float64) - w0  # slope inside the group
-    out = np.full((2, lay.n_out), np.nan)
-    sumw = float(sum(min(j + 1, window - j) for j in range(window)))
-    for x, y, z, w in tasks_b.tolist():
-        if (w & 0xFF) == 0:
-            for i in range(z):
-                seg = AB[:, x + i : x + i + nq]
-                out[:, y + i] = (seg[:, :, 0] * w0 + seg[:, :, 1] * w1).sum(axis=1) / sumw
-        else:
-            out[:, y] = AB[:, x : x + z, 0].sum(axis=1) / flat_genes[w >> 8]
-    chr_pos, want = orc.smooth_by_chromosome(d, var["chromosome"].values, var["start"].values, window, step)
-    np.testing.assert_allclose(out, want, rtol=1e-12, atol=1e-15)
