@@ -65,6 +65,9 @@ int icnv_plan_out_offsets(const icnv_plan* plan, int64_t* out_off_host);
  *   1 = grouped kernel with runtime weights (any step that divides the window);
  *   2 = direct-form kernel staged in parts: any (window, step), float64 centring, any gene-axis length. */
 int icnv_plan_kernel_tier(const icnv_plan* plan);
+/* Cell rows the smoothing kernel chosen for dense input stages per CTA iteration (1, or 2 = row pairs: every gather-table
+ * entry is read once for two rows); < 0 on error. */
+int icnv_plan_rows_per_iteration(const icnv_plan* plan);
 
 /* ------------------------------------------------------- reference profile --
  * Column sums for the reference profile: tl/_infercnv.py:385 (all cells) and

@@ -57,6 +57,7 @@ class DevicePlan:
         if not np.array_equal(off, layout.out_off):  # native window grid vs the host restatement
             raise _lib.IcnvError("internal: native and host output offsets disagree")
         self._ref_keepalive = None
+        self.launches = 0  # kernels launched through this plan (counted per C-ABI call; bench.py's gpu_launches)
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):
@@ -88,11 +89,19 @@ class DevicePlan:
         _lib.check(self.lib.icnv_plan_gather_cost(self.handle, C.byref(w)), "icnv_plan_gather_cost")
         return dict(
             ctas_per_sm=v[0].value, threads=v[1].value, smem_bytes=v[2].value, n_sm=v[3].value, tier=self.tier,
+            rows=int(self.lib.icnv_plan_rows_per_iteration(self.handle)),
             wavefronts_per_gather=round(w.value, 4),
         )
 
     def _stream(self):
         return _lib.stream_handle(self.device)
+
+    @property
+    def table_sets(self) -> int:
+        """Gather-table sets the plan keeps (2 when dense input runs the row-pair kernel and CSR the single-row one):
+        ``icnv_plan_set_reference`` launches one bounds kernel per set."""
+        info = self.launch_info()
+        return 2 if (info["tier"] == 0 and info["rows"] == 2) else 1
 
     # -- reference profile ----------------------------------------------------------------------
     def colsum(self, X, row_cat=None, n_cat: int = 1):
@@ -115,6 +124,7 @@ class DevicePlan:
                 self._stream(),
             )
         _lib.check(rc, "icnv_colsum")
+        self.launches += 2 if isinstance(X, tuple) else 3
         return sums, counts
 
     def mean_from_sums(self, sums, counts, f64: bool = False):
@@ -125,6 +135,7 @@ class DevicePlan:
                 _lib.ptr(sums), _lib.ptr(counts), sums.shape[0], sums.shape[1], _lib.ptr(ref), int(f64), self._stream()
             )
         )
+        self.launches += 1
         return ref
 
     def set_reference(self, ref):
@@ -136,6 +147,7 @@ class DevicePlan:
             self.lib.icnv_plan_set_reference(self.handle, _lib.ptr(ref), ref.shape[0], int(ref.dtype == torch.float64), self._stream()),
             "icnv_plan_set_reference",
         )
+        self.launches += self.table_sets
         self._ref_keepalive = ref
 
     # -- smoothing --------------------------------------------------------------------------------
@@ -163,6 +175,7 @@ class DevicePlan:
                 self.handle, _lib.ptr(X), n, X.stride(0), float(lfc_clip), _lib.ptr(tmp), ld, self._stream()
             )
         _lib.check(rc, "icnv_smooth")
+        self.launches += 1
         return tmp
 
     def center(self, tmp, out=None, row_stats=None, out_dtype=None):
@@ -181,6 +194,7 @@ class DevicePlan:
                 ),
                 "icnv_center_rows",
             )
+            self.launches += 1
         return out, row_stats
 
     def threshold(self, out, row_stats, chunk_rows: int, dynamic_threshold):
@@ -199,7 +213,9 @@ class DevicePlan:
                 self.lib.icnv_chunk_threshold(_lib.ptr(row_stats), n, K, chunk_rows, float(dynamic_threshold), _lib.ptr(thr), self._stream()),
                 "icnv_chunk_threshold",
             )
+            self.launches += 1
         if n > 0:
+            self.launches += 1
             _lib.check(
                 self.lib.icnv_apply_threshold(
                     _lib.ptr(out), is64, n, K, out.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(row_abs), _lib.ptr(row_nnz), self._stream()
@@ -236,15 +252,22 @@ class DevicePlan:
         _lib.check(self.lib.icnv_plan_gene_coverage(self.handle, C.byref(v)), "icnv_plan_gene_coverage")
         return int(v.value)
 
-    def to_csr(self, out, row_nnz):
-        """Dense thresholded block -> device CSR ``(indptr int64, indices int32, data)``."""
+    def to_csr(self, out, row_nnz, indptr=None, indices=None, data=None):
+        """Dense thresholded block -> device CSR ``(indptr int64, indices int32, data)``.  With caller-provided buffers
+        (``indices`` / ``data`` at least nnz long) nothing is read back, so the call stays asynchronous."""
         torch = _torch()
         n, K = out.shape
-        indptr = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
+        if indptr is None:
+            indptr = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
         _lib.check(self.lib.icnv_nnz_to_indptr(_lib.ptr(row_nnz), n, _lib.ptr(indptr), self._stream()), "icnv_nnz_to_indptr")
-        nnz = int(indptr[-1].item())
-        indices = torch.empty((nnz,), dtype=torch.int32, device=self.device)
-        data = torch.empty((nnz,), dtype=out.dtype, device=self.device)
+        self.launches += 1
+        if indices is None:
+            nnz = int(indptr[-1].item())
+            indices = torch.empty((nnz,), dtype=torch.int32, device=self.device)
+            data = torch.empty((nnz,), dtype=out.dtype, device=self.device)
+        else:
+            assert data is not None and data.dtype == out.dtype and indices.dtype == torch.int32
+            nnz = indices.numel()
         if n and nnz:
             _lib.check(
                 self.lib.icnv_dense_to_csr(
@@ -253,6 +276,7 @@ class DevicePlan:
                 ),
                 "icnv_dense_to_csr",
             )
+            self.launches += 1
         return indptr, indices, data
 
 

@@ -25,6 +25,7 @@ SIGNATURES = {
     "icnv_plan_out_width": (C.c_int, [c_vp, c_i64p]),
     "icnv_plan_out_offsets": (C.c_int, [c_vp, c_i64p]),
     "icnv_plan_kernel_tier": (C.c_int, [c_vp]),
+    "icnv_plan_rows_per_iteration": (C.c_int, [c_vp]),
     "icnv_plan_launch_info": (C.c_int, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p]),
     "icnv_colsum_dense_f32": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int32, c_vp, C.c_int32, c_vp, c_vp, c_vp]),
     "icnv_colsum_csr_f32": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int32, c_vp, C.c_int32, c_vp, c_vp, c_vp]),

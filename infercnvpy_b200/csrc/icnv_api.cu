@@ -21,7 +21,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 // aux launchers (icnv_aux.cu)
 int aux_colsum_dense(const float*, int64_t, int64_t, int, const int32_t*, int, double*, int64_t*, double*, int, cudaStream_t);
 int aux_colsum_dense_slots(int* slots);
-int aux_colsum_csr(const int64_t*, const int32_t*, const float*, int64_t, int, const int32_t*, int, double*, int64_t*, cudaStream_t);
+int aux_colsum_csr(const int64_t*, const int32_t*, const float*, int64_t, int, const int32_t*, int, double*, int64_t*, double*, int, cudaStream_t);
 int aux_mean_from_sums(const double*, const int64_t*, int, int, void*, bool, cudaStream_t);
 int aux_nnz_to_indptr(const int32_t*, int64_t, int64_t*, cudaStream_t);
 int aux_build_bounds(const void*, bool, int, int, const int32_t*, int64_t, void*, void*, bool, cudaStream_t);
@@ -106,6 +106,13 @@ struct icnv_plan {
     } tab[2];
     DevBuf<double> alpha, beta, cw;
     DevBuf<Task> tasks_g;
+    // ---- sparse-aware CSR smoothing (icnv_sparse.cu): slot = group * gs + element in position order
+    bool sparse_ok = false;
+    int32_t sp_DP = 0;
+    DevBuf<int32_t> sp_slot_col, sp_col_slot;  // [DP] column of a slot (-1 pad); [G] slot of a column (-1: takes no part)
+    DevBuf<int4> sp_col_tab;                   // [G] {slot, lo, hi, 0}, filled by icnv_plan_set_reference
+    DevBuf<float> sp_zrow;                     // [DP] what a zero entry becomes, filled per smoothing call (depends on lfc_clip)
+    DevBuf<double> c_scratch;  // row pairs with a peak group: third partial sums, [n_sm][2 parities][2 rows][NGpad + PAD_GROUPS]
 
     // ---- direct layout (tier 2); always built
     int32_t n_sorted = 0, n_tasks_d = 0;
@@ -143,6 +150,11 @@ struct icnv_plan {
         beta.release();
         cw.release();
         tasks_g.release();
+        c_scratch.release();
+        sp_slot_col.release();
+        sp_col_slot.release();
+        sp_col_tab.release();
+        sp_zrow.release();
         idx_lin.release();
         lo_lin.release();
         hi_lin.release();
@@ -167,11 +179,13 @@ constexpr size_t SMEM_MAX = 232448;  // 227 KB opt-in limit per CTA on sm_100
 #define ICNV_SMOOTH_ROWS_DEFAULT 2
 #endif
 
-size_t smem_grouped(const icnv_plan& p, int tier, int rows = 1) {
+size_t smem_grouped(const icnv_plan& p, int tier, int rows = 1, bool dbuf = false) {
     size_t s = smooth_scratch_bytes();
     s += (size_t)rows * p.Gpad * 4;
-    s += (size_t)rows * (p.NGpad + PAD_GROUPS) * 16;
-    if (p.qstar >= 0) s += (size_t)rows * (p.NGpad + PAD_GROUPS) * 8;
+    const size_t nbuf = dbuf ? 2 : rows;  // partial-sum buffers: one per staged row, or two parities of a single row
+    s += nbuf * (p.NGpad + PAD_GROUPS) * 16;
+    // the third partial sum of a window with a peak group: shared memory for one row, global (L2) scratch for pairs
+    if (p.qstar >= 0 && !(tier == 0 && rows == 2)) s += nbuf * (p.NGpad + PAD_GROUPS) * 8;
     if (tier == 1) s += (size_t)p.NQ * 16 + (size_t)p.gs * 8;
     return (s + 15) / 16 * 16;
 }
@@ -186,16 +200,37 @@ struct Choice {
     int tier, nwin, gs, tpt;
     size_t smem;
     int rows = 1;  // cell rows staged together per CTA iteration (icnv_smooth.cu, ROWS)
+    bool dbuf = false;  // single row with double-buffered partial sums (icnv_smooth.cu, DBUF)
 };
 
 // Row pairs (ROWS = 2) exist for the templated window-100 kernel; ICNV_SMOOTH_ROWS=1|2 overrides the default.
+int smooth_rows_env() {  // 0 = not set
+    const char* e = std::getenv("ICNV_SMOOTH_ROWS");
+    return (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : 0);
+}
 int smooth_rows_default() {
+    const int v = smooth_rows_env();
+    return v ? v : ICNV_SMOOTH_ROWS_DEFAULT;
+}
+
+// ICNV_SMOOTH_DBUF=0 (developer A/B): single-row kernels keep one partial-sum buffer (two CTAs per SM when they fit)
+bool smooth_dbuf_default() {
     static int v = -1;
     if (v < 0) {
-        const char* e = std::getenv("ICNV_SMOOTH_ROWS");
-        v = (e && e[0] == '2') ? 2 : ((e && e[0] == '1') ? 1 : ICNV_SMOOTH_ROWS_DEFAULT);
+        const char* e = std::getenv("ICNV_SMOOTH_DBUF");
+        v = (e && e[0] == '0') ? 0 : 1;
     }
-    return v;
+    return v == 1;
+}
+
+// ICNV_CSR_SPARSE=0 (developer A/B): CSR input is densified into the staged row of the dense kernels
+bool sparse_csr_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("ICNV_CSR_SPARSE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 // which kernel instantiation runs for this plan + reference dtype
@@ -207,6 +242,9 @@ int choose(const icnv_plan& p, bool c64, Choice* c) {
             if (p.rows == 2) {  // decided at plan creation (the gather tables are laid out for it)
                 c->rows = 2;
                 c->smem = smem_grouped(p, 0, 2);
+            } else if (smooth_dbuf_default() && smem_grouped(p, 0, 1, true) <= SMEM_MAX) {
+                c->dbuf = true;
+                c->smem = smem_grouped(p, 0, 1, true);
             }
             return 0;
         }
@@ -265,6 +303,28 @@ int build_parts(icnv_plan& p, bool c64) {
 }
 
 }  // namespace
+
+// grow-only per-device workspace for the [split][cat][G] partial column sums (stream-ordered use only)
+static int colsum_workspace(size_t need, double** out) {
+    static double* ws[16] = {nullptr};
+    static size_t ws_bytes[16] = {0};
+    int devi = 0;
+    ICNV_CUDA(cudaGetDevice(&devi));
+    if (devi < 0 || devi >= 16) {
+        set_error("column sums: device index out of range");
+        return ICNV_EINVAL;
+    }
+    if (ws_bytes[devi] < need) {
+        if (ws[devi]) {
+            ICNV_CUDA(cudaDeviceSynchronize());  // an earlier launch may still read the old buffer
+            ICNV_CUDA(cudaFree(ws[devi]));
+        }
+        ICNV_CUDA(cudaMalloc(&ws[devi], need));
+        ws_bytes[devi] = need;
+    }
+    *out = ws[devi];
+    return 0;
+}
 
 extern "C" {
 
@@ -410,7 +470,15 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
                     if (pos < Gc) gcol[(size_t)g * gs + j] = p->gene_idx[s0 + pos];
                 }
         }
-        p->permuted = (s == 10 && n == 100) && p->qstar < 0 && gs <= 16 && p->n_tasks_g <= NT && smem_grouped(*p, 0) <= SMEM_MAX;
+        const bool templ_ws = (s == 10 && (n == 100 || n == 250));  // the templated tier-0 instantiations
+        p->permuted = templ_ws && gs <= 16 && p->n_tasks_g <= NT && smem_grouped(*p, 0) <= SMEM_MAX;
+        // non-linear part of the peak group's weights, m_j = cw_j - cw_0 (bits 28..31 of a permuted table entry)
+        std::vector<int> mj(gs, 0);
+        if (p->qstar >= 0)
+            for (int j = 0; j < gs; ++j) {
+                mj[j] = pyr(n, gs * p->qstar + j) - pyr(n, gs * p->qstar);
+                if (mj[j] < 0 || mj[j] > 15) p->permuted = false;
+            }
         std::vector<int32_t> slot_group;
         std::vector<uint8_t> order;
         // ICNV_GATHER_PERM=0 (developer A/B): keep the natural walk; the entries still carry j
@@ -426,7 +494,12 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         const size_t n_entries = (size_t)n_wb * gs * 32 * 4;
         // the kernel that will run decides the unit width: row pairs (templated window 100 that fits twice) walk whole
         // warp-blocks, everything else half warp-blocks
-        const bool pairs = p->permuted && smooth_rows_default() == 2 && smem_grouped(*p, 0, 2) <= SMEM_MAX;
+        // row pairs pay for windows without a peak group (window 100: 0.72 of the HBM roofline vs 0.61-0.66 single);
+        // with one (window 250) the pair kernel measured 3.8 ms / 100k cells vs 2.9 single: phase 3 is 2.5x heavier and
+        // the half-width units leave the gathers latency-bound -> single row with double-buffered partials instead
+        // (ICNV_SMOOTH_ROWS=2 forces pairs)
+        const bool want_pairs = p->qstar < 0 ? smooth_rows_default() == 2 : smooth_rows_env() == 2;
+        const bool pairs = p->permuted && want_pairs && smem_grouped(*p, 0, 2) <= SMEM_MAX;
         p->rows = pairs ? 2 : 1;
         uint32_t raw_base = 0;
         if (smooth_raw_base(&raw_base)) return ICNV_ECUDA;
@@ -436,7 +509,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             return ICNV_EINVAL;
         }
         for (int ts = 0; ts < (pairs ? 2 : 1); ++ts) {
-        const int uw = ts == 0 ? ICNV_UNIT_WIDTH(pairs ? 2 : 1) : ICNV_UNIT_WIDTH(1);
+        const int uw = ts == 0 ? ICNV_UNIT_WIDTH(pairs ? 2 : 1, p->qstar >= 0) : ICNV_UNIT_WIDTH(1, p->qstar >= 0);
         std::vector<uint32_t> off(n_entries, raw_base + (uint32_t)n_genes * 4u);
         std::vector<int32_t> cols(n_entries, -1);
         std::vector<int32_t> grp((size_t)n_wb * 32 * 4, p->NGpad);  // empty slots store their zeros to a pad group
@@ -456,7 +529,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
                             off[e] = raw_base + (uint32_t)col * 4u;
                             cols[e] = col;
                         }
-                        if (p->permuted) off[e] |= (uint32_t)j << 24;  // pads carry their j too (x = 0 either way)
+                        if (p->permuted) off[e] |= ((uint32_t)j << 24) | ((uint32_t)mj[j] << 28);  // pads too (x = 0 either way)
                     }
                 }
         auto& T = p->tab[ts];
@@ -465,6 +538,20 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
             return ICNV_ECUDA;
         }  // table sets
         if (p->alpha.upload(alpha) || p->beta.upload(beta) || p->cw.upload(cw) || p->tasks_g.upload(tasks)) return ICNV_ECUDA;
+        // sparse-aware CSR path: per-slot column and per-column slot of the position-ordered padded row
+        p->sp_DP = p->NGpad * gs;
+        p->sparse_ok = p->permuted && sparse_supported(n, gs) && sparse_smem_bytes(p->sp_DP, p->NGpad, p->qstar >= 0) <= SMEM_MAX;
+        if (p->sparse_ok) {
+            std::vector<int32_t> slot_col((size_t)p->sp_DP, -1), col_slot((size_t)n_genes, -1);
+            for (size_t i = 0; i < gcol.size(); ++i) {
+                slot_col[i] = gcol[i];
+                if (gcol[i] >= 0) col_slot[gcol[i]] = (int32_t)i;
+            }
+            if (p->sp_slot_col.upload(slot_col) || p->sp_col_slot.upload(col_slot) || p->sp_col_tab.alloc((size_t)n_genes) ||
+                p->sp_zrow.alloc((size_t)p->sp_DP))
+                return ICNV_ECUDA;
+        }
+        if (p->permuted && p->qstar >= 0 && p->c_scratch.alloc((size_t)p->n_sm * 8 * (p->NGpad + PAD_GROUPS))) return ICNV_ECUDA;
     }
     if (flat_inv.empty()) flat_inv.push_back(1.0);
     if (p->flat_inv.upload(flat_inv)) return ICNV_ECUDA;
@@ -533,6 +620,13 @@ int icnv_plan_kernel_tier(const icnv_plan* plan) {
     return ch.tier;
 }
 
+int icnv_plan_rows_per_iteration(const icnv_plan* plan) {
+    if (!plan) return ICNV_EINVAL;
+    Choice ch;
+    if (choose(*plan, plan->c64, &ch)) return ICNV_EUNSUPPORTED;
+    return ch.rows;
+}
+
 int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* threads, int32_t* smem_bytes, int32_t* n_sm) {
     if (!plan) return ICNV_EINVAL;
     Choice ch;
@@ -540,11 +634,11 @@ int icnv_plan_launch_info(icnv_plan* plan, int32_t* ctas_per_sm, int32_t* thread
     if (rc) return rc;
     int occ = 1;
     if (ch.tier < 2) {
-        rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
+        rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.dbuf, ch.smem, &occ);
         if (rc) return rc;
     }
     if (ctas_per_sm) *ctas_per_sm = occ;
-    if (threads) *threads = smooth_threads(ch.rows);
+    if (threads) *threads = smooth_threads(ch.rows, ch.dbuf);
     if (smem_bytes) *smem_bytes = (int32_t)ch.smem;
     if (n_sm) *n_sm = plan->n_sm;
     return ICNV_OK;
@@ -562,22 +656,10 @@ int icnv_colsum_dense_f32(const float* X, int64_t n_rows, int64_t ldx, int32_t G
     if (aux_colsum_dense_slots(&slots)) return ICNV_ECUDA;
     const int64_t per_split = (int64_t)std::max(1, (G + 1023) / 1024) * n_cat;
     int n_split = (int)std::min<int64_t>(std::max<int64_t>(1, n_rows / 64), std::max<int64_t>(1, slots / per_split));
-    // grow-only per-device workspace for the [split][cat][G] partial sums (stream-ordered use only)
-    static double* ws[16] = {nullptr};
-    static size_t ws_bytes[16] = {0};
-    int devi = 0;
-    ICNV_CUDA(cudaGetDevice(&devi));
-    const size_t need = sizeof(double) * (size_t)n_split * n_cat * G;
-    if (devi < 0 || devi >= 16) {
-        set_error("icnv_colsum_dense_f32: device index out of range");
-        return ICNV_EINVAL;
-    }
-    if (ws_bytes[devi] < need) {
-        if (ws[devi]) ICNV_CUDA(cudaFree(ws[devi]));
-        ICNV_CUDA(cudaMalloc(&ws[devi], need));
-        ws_bytes[devi] = need;
-    }
-    return aux_colsum_dense(X, n_rows, ldx, G, row_cat, n_cat, sums, counts, ws[devi], n_split, (cudaStream_t)stream);
+    double* ws = nullptr;
+    const int rcw = colsum_workspace(sizeof(double) * (size_t)n_split * n_cat * G, &ws);
+    if (rcw) return rcw;
+    return aux_colsum_dense(X, n_rows, ldx, G, row_cat, n_cat, sums, counts, ws, n_split, (cudaStream_t)stream);
 }
 
 int icnv_colsum_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows, int32_t G,
@@ -586,7 +668,14 @@ int icnv_colsum_csr_f32(const int64_t* indptr, const int32_t* indices, const flo
         set_error("icnv_colsum_csr_f32: bad argument");
         return ICNV_EINVAL;
     }
-    return aux_colsum_csr(indptr, indices, data, n_rows, G, row_cat, n_cat, sums, counts, (cudaStream_t)stream);
+    int devi = 0, n_sm = 148;
+    ICNV_CUDA(cudaGetDevice(&devi));
+    ICNV_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, devi));
+    const int n_split = sparse_colsum_splits(n_rows, n_sm);
+    double* ws = nullptr;
+    int rc = colsum_workspace(sizeof(double) * (size_t)n_split * n_cat * G, &ws);
+    if (rc) return rc;
+    return aux_colsum_csr(indptr, indices, data, n_rows, G, row_cat, n_cat, sums, counts, ws, n_split, (cudaStream_t)stream);
 }
 
 int icnv_mean_from_sums(const double* sums, const int64_t* counts, int32_t n_cat, int32_t G, void* ref_out, int32_t out_is_f64,
@@ -614,6 +703,7 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
             if (plan->tab[ts].uw)
                 rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->tab[ts].cols_w.ptr, (int64_t)plan->tab[ts].cols_w.n,
                                       plan->tab[ts].lo_w.ptr, plan->tab[ts].hi_w.ptr, false, st);
+        if (!rc && plan->sparse_ok) rc = sparse_col_table_launch(ref, false, n_cat, plan->G, plan->sp_col_slot.ptr, plan->sp_col_tab.ptr, st);
     } else {
         rc = aux_build_bounds(ref, c64, n_cat, plan->G, plan->idx_lin.ptr, plan->n_sorted, plan->lo_lin.ptr,
                               plan->hi_lin.ptr, c64, st);
@@ -685,6 +775,15 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
         const int grid = (int)std::min<int64_t>(sp.n_rows, (int64_t)plan->n_sm);
         return direct_launch(dp, plan->bounded, plan->c64, grid, plan->parts_smem[k], (cudaStream_t)stream);
     }
+    if (!sp.X && ch.tier == 0 && plan->sparse_ok && sparse_csr_default()) {
+        // CSR input: scatter the stored entries over the constant row instead of densifying in matrix order
+        rc = sparse_zrow_launch(plan->sp_slot_col.ptr, plan->sp_DP, plan->sp_col_tab.ptr, (float)lfc_clip, plan->bounded, plan->sp_zrow.ptr,
+                                (cudaStream_t)stream);
+        if (rc) return rc;
+        return sparse_smooth_launch(plan->window, plan->gs, plan->bounded, sp.indptr, sp.indices, sp.data, sp.n_rows, plan->sp_col_tab.ptr,
+                                    plan->sp_zrow.ptr, plan->sp_DP, plan->NG, plan->NGpad, plan->inv_sumw, plan->flat_inv.ptr,
+                                    plan->tasks_g.ptr, plan->n_tasks_g, (float)lfc_clip, out, ldo, plan->n_sm, (cudaStream_t)stream);
+    }
     sp.G = plan->G;
     sp.Gpad = plan->Gpad;
     sp.gs = plan->gs;
@@ -706,6 +805,7 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
     sp.alpha = plan->alpha.ptr;
     sp.beta = plan->beta.ptr;
     sp.cw = plan->cw.ptr;
+    sp.c_scratch = plan->c_scratch.ptr;
     sp.clip = plan->c64 ? lfc_clip : (double)(float)lfc_clip;
     sp.clipf = (float)lfc_clip;
     sp.inv_sumw = plan->inv_sumw;
@@ -724,15 +824,19 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
         const char* e2 = std::getenv("ICNV_SPLIT_ROWS");
         sp.split_rows = (e2 && e2[0] == '0') ? 0 : 1;
     }
+    if (ch.dbuf && !sp.use_tma) {  // the double-buffered kernel overlaps TMA fills with phase 3; other inputs keep two CTAs per SM
+        ch.dbuf = false;
+        ch.smem = smem_grouped(*plan, 0, 1);
+    }
     int occ = 0;
-    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.smem, &occ);
+    rc = smooth_occupancy(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.dbuf, ch.smem, &occ);
     if (rc) return rc;
     if (occ < 1) {
         set_error("smooth: kernel does not fit on an SM");
         return ICNV_EUNSUPPORTED;
     }
     const int grid = (int)std::min<int64_t>((sp.n_rows + ch.rows - 1) / ch.rows, (int64_t)plan->n_sm * occ);
-    return smooth_launch(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, sp, grid, ch.smem, (cudaStream_t)stream);
+    return smooth_launch(ch.tier, ch.nwin, ch.gs, plan->bounded, plan->c64, ch.tpt, ch.rows, ch.dbuf, sp, grid, ch.smem, (cudaStream_t)stream);
 }
 
 int icnv_smooth_dense_f32(icnv_plan* plan, const float* X, int64_t n_rows, int64_t ldx, double lfc_clip, double* tmp,

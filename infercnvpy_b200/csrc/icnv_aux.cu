@@ -66,23 +66,7 @@ __global__ void __launch_bounds__(256, 4) colsum_dense_kernel(const float* __res
         if (col[u] < G) dst[col[u]] = acc[u];
 }
 
-// CSR variant: one warp per row chunk, atomics into a [cat][G] fp64 accumulator per split.
-__global__ void __launch_bounds__(256) colsum_csr_kernel(const int64_t* __restrict__ indptr,
-                                                         const int32_t* __restrict__ indices,
-                                                         const float* __restrict__ data, int64_t n_rows, int G,
-                                                         const int32_t* __restrict__ row_cat, int n_cat,
-                                                         double* __restrict__ sums) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp; r < n_rows; r += n_warps) {
-        const int cat = row_cat ? row_cat[r] : 0;
-        if (cat < 0 || cat >= n_cat) continue;
-        const int64_t e0 = indptr[r], e1 = indptr[r + 1];
-        for (int64_t e = e0 + lane; e < e1; e += 32) atomicAdd(sums + (size_t)cat * G + indices[e], (double)data[e]);
-    }
-}
-
+// (the CSR column sums live in icnv_sparse.cu: deterministic, no atomics)
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_split, int64_t n, double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -827,9 +811,11 @@ int aux_colsum_dense(const float* X, int64_t n_rows, int64_t ldx, int G, const i
 }
 
 int aux_colsum_csr(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows, int G,
-                   const int32_t* row_cat, int n_cat, double* sums, int64_t* counts, cudaStream_t st) {
-    ICNV_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)n_cat * G, st));
-    colsum_csr_kernel<<<grid_for_rows(n_rows), 256, 0, st>>>(indptr, indices, data, n_rows, G, row_cat, n_cat, sums);
+                   const int32_t* row_cat, int n_cat, double* sums, int64_t* counts, double* partial, int n_split, cudaStream_t st) {
+    int rc = sparse_colsum_launch(indptr, indices, data, n_rows, G, row_cat, n_cat, partial, n_split, st);
+    if (rc) return rc;
+    const int64_t n = (int64_t)n_cat * G;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, n_split, n, sums);
     ICNV_CUDA(cudaGetLastError());
     ICNV_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * n_cat, st));
     count_rows_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(row_cat, n_rows, n_cat,

@@ -12,9 +12,15 @@ namespace icnv {
 constexpr int NT = 512;         // threads per CTA of the smoothing kernel
 constexpr int NW = NT / 32;     // warps per CTA
 // threads per CTA of the smoothing kernel that stages `rows` cell rows per iteration
-__host__ __device__ constexpr int smooth_threads(int rows) { return NT + 0 * rows; }
+// the double-buffered single-row kernel has no hand-over barriers: extra warps are pure gather capacity (ICNV_DBUF_THREADS)
+#ifndef ICNV_DBUF_THREADS
+#define ICNV_DBUF_THREADS 768
+#endif
+__host__ __device__ constexpr int smooth_threads(int rows, bool dbuf = false) { return dbuf ? ICNV_DBUF_THREADS : NT + 0 * rows; }
 // groups per lane of one phase-2 work unit (table layout [unit][step][lane][u < width]) for a kernel staging `rows` rows
-#define ICNV_UNIT_WIDTH(rows) ((rows) == 2 ? 4 : 2)
+// Row pairs of a window whose pyramid peak falls inside a group (third partial sum per group) keep half units: 12 fp64
+// accumulators per lane instead of 16 + 8.
+#define ICNV_UNIT_WIDTH(rows, peak_group) (((rows) == 2 && !(peak_group)) ? 4 : 2)
 #ifndef ICNV_LOUT
 #define ICNV_LOUT 9
 #endif
@@ -66,6 +72,10 @@ struct SmoothParams {
     const double* alpha;    // [NQ] weight of A_g = sum_j x
     const double* beta;     // [NQ] weight of B_g = sum_j j*x
     const double* cw;       // [gs] weights inside the peak group (C_g = sum_j cw_j x)
+    // Row pairs with a peak group: the third partial sum C'_g = sum_j (cw_j - cw_0) x_j of both staged rows does not fit
+    // in shared memory next to 2 x (row + A/B partials); it goes through a per-CTA global scratch that stays in L2,
+    // double-buffered by iteration parity: [grid][2 parities][2 rows][NGpad + PAD_GROUPS]
+    double* c_scratch;
     // ---- common
     double clip;
     float clipf;
@@ -161,6 +171,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// same without an L2 cache hint
+__device__ __forceinline__ void bulk_g2s_plain(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 // named barriers: `count` threads (a multiple of 32) take part; arrive does not block
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -210,9 +231,9 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 // Launchers implemented in icnv_smooth.cu
-int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, const SmoothParams& p, int grid,
+int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, bool dbuf, const SmoothParams& p, int grid,
                   size_t smem, cudaStream_t stream);
-int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm);
+int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, bool dbuf, size_t smem, int* ctas_per_sm);
 
 int direct_launch(const DirectParams& p, bool bounded, bool c64, int grid, size_t smem, cudaStream_t st);
 int center_wide_launch(const double* tmp, int64_t n_rows, int64_t ld, const int32_t* kaddr, int K, void* out, bool f64, int64_t ldo,
@@ -221,5 +242,16 @@ int center_wide_launch(const double* tmp, int64_t n_rows, int64_t ld, const int3
 double schedule_gathers(const std::vector<int32_t>& gcol, int NG, int gs, int n_genes, int nsets, bool permute,
                         std::vector<int32_t>& slot_group, std::vector<uint8_t>& order);
 int genevals_launch(const GeneValParams& p, int grid, size_t smem, cudaStream_t st);
+// icnv_sparse.cu: sparse-aware smoothing of CSR input + deterministic CSR column sums
+bool sparse_supported(int nwin, int gs);
+size_t sparse_smem_bytes(int DP, int NGpad, bool peak_group);
+int sparse_zrow_launch(const int32_t* slot_col, int n_slots, const int4* col_tab, float clipf, bool bounded, float* zrow, cudaStream_t st);
+int sparse_col_table_launch(const void* ref, bool ref_f64, int n_cat, int G, const int32_t* col_slot, int4* col_tab, cudaStream_t st);
+int sparse_smooth_launch(int nwin, int gs, bool bounded, const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                         const int4* col_tab, const float* zrow, int DP, int NG, int NGpad, double inv_sumw, const double* flat_inv,
+                         const Task* tasks, int n_tasks, float clipf, double* out, int64_t ldo, int n_sm, cudaStream_t st);
+int sparse_colsum_splits(int64_t n_rows, int n_sm);
+int sparse_colsum_launch(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows, int G, const int32_t* row_cat,
+                         int n_cat, double* partial, int n_split, cudaStream_t st);
 
 }  // namespace icnv

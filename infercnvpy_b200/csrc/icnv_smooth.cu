@@ -44,10 +44,15 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 // ROWS = cell rows staged and gathered together per CTA iteration (grouped tiers only).  ROWS == 2 reads every
 // gather-table entry once for two rows — the tables (160 KB per sweep, L2 -> L1) are the largest removable share of the
 // kernel's l1tex work — at the price of one CTA per SM (2 x 80 KB of staged rows + 2 x 32 KB of partials).
-template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS>
-__global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 && ROWS == 1) ? 2 : 1) smooth_kernel(const SmoothParams p) {
+// DBUF (single staged row only): the partial sums are double-buffered by iteration parity, so warps that own no outputs
+// gather the WHOLE next row while the group warps are still in phase 3 — no hand-over barriers at all.  One CTA per SM
+// (row + 2 x partials), which is how the window-250 kernel (third partial sum per group, no room for row pairs) runs.
+template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS, bool DBUF>
+__global__ void __launch_bounds__(smooth_threads(ROWS, DBUF), (TIER == 0 && TPT == 1 && ROWS == 1 && !DBUF && (NWIN / 2) % (GS > 0 ? GS : 1) == 0) ? 2 : 1)
+    smooth_kernel(const SmoothParams p) {
+    static_assert(!DBUF || ROWS == 1, "double-buffered partial sums exist for the single-row kernel");
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NTH = smooth_threads(ROWS), NWH = NTH / 32;  // row pairs run 32 warps (64 registers each)
+    constexpr int NTH = smooth_threads(ROWS, DBUF), NWH = NTH / 32;  // row pairs run 32 warps (64 registers each)
     Scratch* sc = reinterpret_cast<Scratch*>(smem);
     unsigned char* carve = smem + SCRATCH_BYTES;
 
@@ -66,9 +71,12 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
     constexpr int VPT = TPT * LOUT;
     // groups per lane in one phase-2 work unit.  Row pairs keep whole warp-blocks: a run-ahead warp can only gather ONE
     // unit before it has to wait for the partial-sum buffer, so bigger units overlap more of phase 3.
-    constexpr int UW = ICNV_UNIT_WIDTH(ROWS);
-    // permuted walk (icnv_schedule.cu): step t of a lane reads element j = entry >> 24 of its group, not element t
-    constexpr bool PERM = (TIER == 0) && !M3_C;
+    constexpr int UW = ICNV_UNIT_WIDTH(ROWS, M3_C);
+    // permuted walk (icnv_schedule.cu): step t of a lane reads element j = (entry >> 24) & 15 of its group, not element t;
+    // with a peak group bits 28..31 carry m_j = cw_j - cw_0, the non-linear part of the weights inside that group
+    constexpr bool PERM = (TIER == 0);
+    // row pairs with a peak group: the third partial sum lives in a global (L2) scratch, see SmoothParams::c_scratch
+    constexpr bool CGLOBAL = M3_C && ROWS == 2;
 #define ICNV_ABS (p.NGpad + PAD_GROUPS) /* partial-sum slots per staged row */
 
     // ---- carve shared memory
@@ -85,10 +93,12 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
         raw = reinterpret_cast<float*>(carve);
         carve += (size_t)ROWS * p.Gpad * 4;
         AB = reinterpret_cast<double2*>(carve);
-        carve += (size_t)ROWS * ICNV_ABS * 16;
-        if ((TIER == 0) ? M3_C : (p.qstar >= 0)) {
+        carve += (size_t)(DBUF ? 2 : ROWS) * ICNV_ABS * 16;
+        if constexpr (CGLOBAL) {
+            Cp = p.c_scratch + (size_t)blockIdx.x * 2 * ROWS * ICNV_ABS;
+        } else if ((TIER == 0) ? M3_C : (p.qstar >= 0)) {
             Cp = reinterpret_cast<double*>(carve);
-            carve += (size_t)ROWS * ICNV_ABS * 8;
+            carve += (size_t)(DBUF ? 2 : ROWS) * ICNV_ABS * 8;
         }
         if constexpr (TIER == 1) {
             w_alpha = reinterpret_cast<double*>(carve);
@@ -109,6 +119,11 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
             for (int i = p.NG + tid; i < ICNV_ABS; i += NTH) {
                 AB[(ROWS > 1 ? rr * ICNV_ABS : 0) + i] = make_double2(0.0, 0.0);
                 if (Cp) Cp[(ROWS > 1 ? rr * ICNV_ABS : 0) + i] = 0.0;
+                if constexpr (CGLOBAL) Cp[(ROWS + rr) * ICNV_ABS + i] = 0.0;  // second parity buffer
+                if constexpr (DBUF) {
+                    AB[ICNV_ABS + i] = make_double2(0.0, 0.0);
+                    if (Cp) Cp[ICNV_ABS + i] = 0.0;
+                }
             }
         }
         if constexpr (TIER == 1) {
@@ -228,7 +243,8 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
             // work units are handed out dynamically: warps that are not in the group arrive here early (they skipped
             // phase 3 of the previous iteration) and take most of them
             int* next_wb = &sc->next_wb[it & 1];
-            bool handed_over = in_group || it == 0;  // group warps synchronise on barrier 2 after their phase 3
+            bool handed_over = DBUF || in_group || it == 0;  // group warps synchronise on barrier 2 after their phase 3
+            const int pbuf = DBUF ? (it & 1) * ICNV_ABS : 0;  // partial-sum buffer of this iteration
             while (true) {
                 int wb = 0;
                 if (lane == 0) wb = atomicAdd(next_wb, 1);
@@ -269,12 +285,13 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                         h4[0] = hi.x, h4[1] = hi.y;
                     }
                     float x[ROWS][UW];
-                    double jd[UW];
+                    double jd[UW], md[UW];
                     if constexpr (PERM) {
 #pragma unroll
                         for (int u = 0; u < UW; ++u) {
                             // exact int -> double without I2F: 2^52 + j carries j in the low mantissa bits
-                            jd[u] = __hiloint2double(0x43300000, (int)(ad[u] >> 24)) - 4503599627370496.0;
+                            jd[u] = __hiloint2double(0x43300000, (int)((ad[u] >> 24) & 15u)) - 4503599627370496.0;
+                            if constexpr (M3_C) md[u] = __hiloint2double(0x43300000, (int)(ad[u] >> 28)) - 4503599627370496.0;
                             ad[u] &= 0x00FFFFFFu;
                         }
                     }
@@ -299,20 +316,22 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                             if (TIER == 0 && j == 0) {  // first step of the (unrolled) walk: no add to zero
                                 a[rr][u] = dd;
                                 if constexpr (PERM) b[rr][u] = jd[u] * dd;
-                                if (qstar >= 0) c[rr][u] = cwj * dd;
+                                if constexpr (PERM && M3_C) c[rr][u] = md[u] * dd;
+                                else if (qstar >= 0) c[rr][u] = cwj * dd;
                             } else {
                                 a[rr][u] += dd;
                                 if constexpr (PERM)
                                     b[rr][u] = fma(jd[u], dd, b[rr][u]);
                                 else if (j > 0)
                                     b[rr][u] = fma((double)j, dd, b[rr][u]);
-                                if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
+                                if constexpr (PERM && M3_C) c[rr][u] = fma(md[u], dd, c[rr][u]);
+                                else if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
                             }
                         }
                 };
                 if constexpr (TIER == 0) {
 #pragma unroll
-                    for (int j = 0; j < GS; ++j) body(j, M3_C ? (double)pyr(NWIN, GS * (QSTAR_C < 0 ? 0 : QSTAR_C) + j) : 0.0);
+                    for (int j = 0; j < GS; ++j) body(j, 0.0);
                 } else {
                     for (int j = 0; j < gs; ++j) body(j, w_c[j]);
                 }
@@ -333,8 +352,11 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                 for (int rr = 0; rr < ROWS; ++rr)
 #pragma unroll
                     for (int u = 0; u < UW; ++u) {
-                        AB[(ROWS > 1 ? rr * ICNV_ABS : 0) + gq[u]] = make_double2(a[rr][u], b[rr][u]);
-                        if (qstar >= 0) Cp[(ROWS > 1 ? rr * ICNV_ABS : 0) + gq[u]] = c[rr][u];
+                        AB[(ROWS > 1 ? rr * ICNV_ABS : pbuf) + gq[u]] = make_double2(a[rr][u], b[rr][u]);
+                        if constexpr (CGLOBAL)
+                            __stcg(Cp + ((it & 1) * ROWS + rr) * ICNV_ABS + gq[u], c[rr][u]);
+                        else if (qstar >= 0)
+                            Cp[(ROWS > 1 ? rr * ICNV_ABS : pbuf) + gq[u]] = c[rr][u];
                     }
             }
             if (!handed_over) named_bar_sync(1, NTH);  // took no warp-block this time: keep the barrier count whole
@@ -360,8 +382,9 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
         for (int rr = my_rr; rr < ROWS; rr += (split_rows ? ROWS : 1)) {
         const bool last_rr = split_rows || rr == ROWS - 1;
         const bool row_exists = ROWS == 1 || row + rr < p.n_rows;  // odd tail: the pair's second row does not exist
-        const double2* ABr = AB + (ROWS > 1 ? rr * ICNV_ABS : 0);
-        const double* Cpr = Cp + (ROWS > 1 ? rr * ICNV_ABS : 0);
+        const int pbuf3 = DBUF ? (it & 1) * ICNV_ABS : 0;
+        const double2* ABr = AB + (ROWS > 1 ? rr * ICNV_ABS : pbuf3);
+        const double* Cpr = Cp + (CGLOBAL ? ((it & 1) * ROWS + rr) * ICNV_ABS : (ROWS > 1 ? rr * ICNV_ABS : pbuf3));
         // ======================= windows =======================
         double v[VPT];
         int nv[TPT];
@@ -378,7 +401,18 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                     if constexpr (TIER == 0) {
                         double acc[LOUT];
 #pragma unroll
-                        for (int i = 0; i < LOUT; ++i) acc[i] = 0.0;
+                        for (int i = 0; i < LOUT; ++i) {
+                            // the peak group's non-linear part C' (its linear part c0 * A rides in the loop below);
+                            // from the L2 scratch these loads are issued first and consumed last
+                            acc[i] = 0.0;
+                        }
+                        // the peak group's non-linear part C' (its linear part c0 * A rides in the loop below): from the
+                        // L2 scratch these loads are issued first and consumed after the loop
+                        double cpk[M3_C ? LOUT : 1];
+                        if constexpr (M3_C) {
+#pragma unroll
+                            for (int i = 0; i < LOUT; ++i) cpk[i] = CGLOBAL ? __ldcg(Cpr + t.x + QSTAR_C + i) : Cpr[t.x + QSTAR_C + i];
+                        }
                         const double2* P = ABr + t.x;
 #pragma unroll
                         for (int q = 0; q < NQ_C + LOUT - 1; ++q) {
@@ -386,9 +420,9 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
 #pragma unroll
                             for (int i = 0; i < LOUT; ++i) {
                                 const int w = q - i;
-                                if (w >= 0 && w < NQ_C && w != QSTAR_C) {
+                                if (w >= 0 && w < NQ_C) {
                                     const int al = pyr(NWIN, GS * w);
-                                    const int be = GS > 1 ? pyr(NWIN, GS * w + 1) - al : 0;
+                                    const int be = (GS > 1 && w != QSTAR_C) ? pyr(NWIN, GS * w + 1) - al : 0;
                                     acc[i] = fma((double)al, ab.x, acc[i]);
                                     if (be == 1)
                                         acc[i] += ab.y;
@@ -399,7 +433,7 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
                         }
                         if constexpr (M3_C) {
 #pragma unroll
-                            for (int i = 0; i < LOUT; ++i) acc[i] += Cpr[t.x + QSTAR_C + i];
+                            for (int i = 0; i < LOUT; ++i) acc[i] += cpk[i];
                         }
 #pragma unroll
                         for (int i = 0; i < LOUT; ++i)
@@ -432,7 +466,7 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
 
         ICNV_STAMP(15);
         {
-            if (last_rr) {  // all partials this thread needs are in registers: hand the buffer over
+            if (last_rr && !DBUF) {  // all partials this thread needs are in registers: hand the buffer over
                 named_bar_arrive(1, NTH);
                 named_bar_sync(2, n_group);
             }
@@ -477,19 +511,19 @@ __global__ void __launch_bounds__(smooth_threads(ROWS), (TIER == 0 && TPT == 1 &
 
 // ------------------------------------------------------------------------------------------------
 // instantiation table
-template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS = 1>
+template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS = 1, bool DBUF = false>
 static int launch_one(const SmoothParams& p, int grid, size_t smem, cudaStream_t stream) {
-    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS>;
+    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS, DBUF>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, smooth_threads(ROWS), smem, stream>>>(p);
+    k<<<grid, smooth_threads(ROWS, DBUF), smem, stream>>>(p);
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }
-template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS = 1>
+template <int TIER, int NWIN, int GS, bool BOUNDED, bool C64, int TPT, int ROWS = 1, bool DBUF = false>
 static int occ_one(size_t smem, int* out) {
-    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS>;
+    auto k = smooth_kernel<TIER, NWIN, GS, BOUNDED, C64, TPT, ROWS, DBUF>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, smooth_threads(ROWS), smem));
+    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, smooth_threads(ROWS, DBUF), smem));
     return 0;
 }
 
@@ -498,7 +532,17 @@ static int occ_one(size_t smem, int* out) {
         if (tier == 0 && nwin == 100 && gs == 10 && tpt == 1 && rows == 2) {                               \
             return bounded ? FN<0, 100, 10, true, false, 1, 2>(__VA_ARGS__) : FN<0, 100, 10, false, false, 1, 2>(__VA_ARGS__); \
         }                                                                                                  \
+        if (tier == 0 && nwin == 250 && gs == 10 && tpt == 1 && rows == 2) {                               \
+            return bounded ? FN<0, 250, 10, true, false, 1, 2>(__VA_ARGS__) : FN<0, 250, 10, false, false, 1, 2>(__VA_ARGS__); \
+        }                                                                                                  \
         if (rows != 1) break;                                                                              \
+        if (tier == 0 && nwin == 100 && gs == 10 && tpt == 1 && dbuf) {                                    \
+            return bounded ? FN<0, 100, 10, true, false, 1, 1, true>(__VA_ARGS__) : FN<0, 100, 10, false, false, 1, 1, true>(__VA_ARGS__); \
+        }                                                                                                  \
+        if (tier == 0 && nwin == 250 && gs == 10 && tpt == 1 && dbuf) {                                    \
+            return bounded ? FN<0, 250, 10, true, false, 1, 1, true>(__VA_ARGS__) : FN<0, 250, 10, false, false, 1, 1, true>(__VA_ARGS__); \
+        }                                                                                                  \
+        if (dbuf) break;                                                                                   \
         if (tier == 0 && nwin == 100 && gs == 10 && tpt == 1) {                                            \
             return bounded ? FN<0, 100, 10, true, false, 1>(__VA_ARGS__) : FN<0, 100, 10, false, false, 1>(__VA_ARGS__); \
         }                                                                                                  \
@@ -513,13 +557,13 @@ static int occ_one(size_t smem, int* out) {
         }                                                                                                  \
     } while (0)
 
-int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, const SmoothParams& p, int grid,
+int smooth_launch(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, bool dbuf, const SmoothParams& p, int grid,
                   size_t smem, cudaStream_t stream) {
     ICNV_DISPATCH(launch_one, p, grid, smem, stream);
     set_error("smooth_launch: no kernel instantiation for this configuration");
     return -3;
 }
-int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, size_t smem, int* ctas_per_sm) {
+int smooth_occupancy(int tier, int nwin, int gs, bool bounded, bool c64, int tpt, int rows, bool dbuf, size_t smem, int* ctas_per_sm) {
     ICNV_DISPATCH(occ_one, smem, ctas_per_sm);
     set_error("smooth_occupancy: no kernel instantiation for this configuration");
     return -3;

@@ -23,7 +23,7 @@ with DevicePlan(layout, dev) as plan:
     plan.smooth(Xd, 3.0); torch.cuda.synchronize()
     lib.icnv_debug_set_timeline(None, 0)
 t = buf.cpu().numpy().astype(np.float64)
-ROWS = 2 if (info['ctas_per_sm'] == 1 and info['tier'] == 0 and window == 100) else 1
+ROWS = info.get('rows', 1)
 rows = slice(4, min(R, N // (grid * ROWS) - 2))   # steady state (iterations; an iteration stages ROWS rows)
 T = t[:, rows, :]
 def d(a, b): x = (T[..., b] - T[..., a]).ravel(); x = x[(T[..., a].ravel() > 0) & (T[..., b].ravel() > 0)]; return float(np.median(x)), float(np.mean(x))
