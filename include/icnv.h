@@ -179,19 +179,28 @@ int icnv_gram_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, double*
 /* Y [n_rows, n_comp] float32 = (X - mu) V;  V [K, n_comp] float64 row-major, mu [K] float64 or NULL */
 int icnv_project_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, const double* V, int32_t n_comp,
                      const double* mu, float* Y, void* stream);
-/* exact euclidean kNN of rows [q0, q0+nq) of P [n_all, d] float32 against all rows: KK = 16 (k <= 16) or 32
- * neighbours per query, ascending squared distance, ties by index; knn_idx/knn_d2 are [nq, KK] */
-int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx,
-                 float* knn_d2, void* stream);
+/* Exact euclidean kNN of rows [q0, q0+nq) of P [n_all, d <= 64] float32 (row pitch ld) against all rows, as a tensor-core
+ * distance GEMM (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM) + exact fp64 re-rank of k + slack candidates
+ * per query (csrc/icnv_knn.cu).  k <= 20; q0 must be a multiple of 128.  knn_idx / knn_d2 are [nq, out_ld]: the k nearest
+ * by ascending squared distance, ties by index (column 0 is the query itself).  workspace: icnv_knn_workspace_bytes. */
+int64_t icnv_knn_workspace_bytes(int64_t n_all, int64_t nq);
+int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t ld, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx,
+                 float* knn_d2, int32_t out_ld, void* workspace, void* stream);
 /* umap-learn smooth_knn_dist + membership strengths per row; dist/idx/vals are [n, k] */
 int icnv_fuzzy_rows(const float* dist, const int32_t* idx, int64_t n, int32_t k, int64_t row0, float mean_all,
                     float* vals, float* sigma, float* rho, void* stream);
-/* weighted degree of a CSR graph, and one synchronous local-moving sweep of RB-configuration modularity
- * (ctot is scratch [n]; n_moved receives the number of nodes that changed community) */
+/* Weighted degree of a CSR graph (both directions stored), and ONE synchronous sweep of the Leiden scheme on it
+ * (csrc/icnv_graph.cu) with the RB-configuration quality (gamma * k_i * K_c / 2m).  bound == NULL: local moving (nodes
+ * move to the best neighbouring community of `comm`); bound != NULL: refinement — only singletons of `comm` that are well
+ * connected to their community `bound` move, and only to sub-communities of the same bound with a positive gain.
+ * Half of the nodes (hash of node and sweep) may move per sweep.  work: icnv_community_sweep_work_bytes(n) bytes of
+ * scratch; stats: int32[3] = {nodes moved, nodes handled by the hash-table path, table overflow flag (then the sweep is
+ * incomplete: treat as ICNV_EUNSUPPORTED)}.  Any node degree is handled exactly. */
 int icnv_weighted_degree(const int64_t* indptr, const float* w, int64_t n, double* kdeg, void* stream);
-int icnv_louvain_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg,
-                       const int32_t* comm, double* ctot, int64_t n, double two_m, double gamma, int32_t sweep,
-                       int32_t* comm_new, int32_t* n_moved, void* stream);
+int64_t icnv_community_sweep_work_bytes(int64_t n);
+int icnv_community_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg, const int32_t* comm,
+                         const int32_t* bound, int64_t n, double two_m, double gamma, int32_t sweep, void* work, int32_t* comm_new,
+                         int32_t* stats, void* stream);
 
 /* Launch geometry of the smoothing kernel chosen for this plan (for the bench
  * and the ncu notes): CTAs per SM, threads, dynamic shared memory bytes. */

@@ -38,11 +38,12 @@ int aux_row_corrcoef(const double*, int64_t, int64_t, int, double*, int64_t, dou
 int graph_csr_to_dense(const int64_t*, const int32_t*, const void*, bool, int64_t, int, float*, int64_t, cudaStream_t);
 int graph_gram(const float*, int64_t, int64_t, int, double*, cudaStream_t);
 int graph_project(const float*, int64_t, int64_t, int, const double*, int, const double*, float*, cudaStream_t);
-int graph_knn(const float*, int64_t, int, int64_t, int64_t, int, int32_t*, float*, cudaStream_t);
+int knn_launch(const float*, int64_t, int, int64_t, int64_t, int64_t, int, int, int32_t*, float*, void*, cudaStream_t);
+size_t knn_workspace_bytes(int64_t, int64_t);
 int graph_fuzzy_rows(const float*, const int32_t*, int64_t, int, int64_t, float, float*, float*, float*, cudaStream_t);
 int graph_weighted_degree(const int64_t*, const float*, int64_t, double*, cudaStream_t);
-int graph_louvain_sweep(const int64_t*, const int32_t*, const float*, const double*, const int32_t*, double*, int64_t, double, double,
-                        int, int32_t*, int32_t*, cudaStream_t);
+int graph_community_sweep(const int64_t*, const int32_t*, const float*, const double*, const int32_t*, const int32_t*, int64_t, double,
+                          double, int, void*, int32_t*, int32_t*, cudaStream_t);
 
 template <typename T>
 struct DevBuf {
@@ -1023,10 +1024,17 @@ int icnv_project_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, cons
     if (!X || !V || !Y || n_comp < 1) return ICNV_EINVAL;
     return graph_project(X, n_rows, ld, K, V, n_comp, mu, Y, (cudaStream_t)stream);
 }
-int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx, float* knn_d2,
-                 void* stream) {
-    if (!P || !knn_idx || !knn_d2 || q0 < 0 || q0 + nq > n_all) return ICNV_EINVAL;
-    return graph_knn(P, n_all, d, q0, nq, k, knn_idx, knn_d2, (cudaStream_t)stream);
+int64_t icnv_knn_workspace_bytes(int64_t n_all, int64_t nq) {
+    if (n_all < 0 || nq < 0) return -1;
+    return (int64_t)knn_workspace_bytes(n_all, nq);
+}
+int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t ld, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx, float* knn_d2,
+                 int32_t out_ld, void* workspace, void* stream) {
+    if (!P || !knn_idx || !knn_d2 || !workspace || q0 < 0 || q0 + nq > n_all || d < 1 || ld < d || k < 1 || out_ld < k) {
+        set_error("icnv_knn_f32: bad argument");
+        return ICNV_EINVAL;
+    }
+    return knn_launch(P, n_all, d, ld, q0, nq, k, out_ld, knn_idx, knn_d2, workspace, (cudaStream_t)stream);
 }
 int icnv_fuzzy_rows(const float* dist, const int32_t* idx, int64_t n, int32_t k, int64_t row0, float mean_all, float* vals,
                     float* sigma, float* rho, void* stream) {
@@ -1037,11 +1045,15 @@ int icnv_weighted_degree(const int64_t* indptr, const float* w, int64_t n, doubl
     if (!indptr || !kdeg) return ICNV_EINVAL;
     return graph_weighted_degree(indptr, w, n, kdeg, (cudaStream_t)stream);
 }
-int icnv_louvain_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg, const int32_t* comm,
-                       double* ctot, int64_t n, double two_m, double gamma, int32_t sweep, int32_t* comm_new, int32_t* n_moved,
-                       void* stream) {
-    if (!indptr || !kdeg || !comm || !ctot || !comm_new || !n_moved || !(two_m > 0)) return ICNV_EINVAL;
-    return graph_louvain_sweep(indptr, indices, w, kdeg, comm, ctot, n, two_m, gamma, sweep, comm_new, n_moved, (cudaStream_t)stream);
+int64_t icnv_community_sweep_work_bytes(int64_t n) { return n < 0 ? -1 : (int64_t)(n * 24 + 64); }
+int icnv_community_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg, const int32_t* comm,
+                         const int32_t* bound, int64_t n, double two_m, double gamma, int32_t sweep, void* work, int32_t* comm_new,
+                         int32_t* stats, void* stream) {
+    if (!indptr || !kdeg || !comm || !work || !comm_new || !stats || !(two_m > 0)) {
+        set_error("icnv_community_sweep: bad argument");
+        return ICNV_EINVAL;
+    }
+    return graph_community_sweep(indptr, indices, w, kdeg, comm, bound, n, two_m, gamma, sweep, work, comm_new, stats, (cudaStream_t)stream);
 }
 
 }  // extern "C"

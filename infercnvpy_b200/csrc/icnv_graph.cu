@@ -129,92 +129,6 @@ __global__ void __launch_bounds__(256) project_kernel(const float* __restrict__ 
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Exact k nearest neighbours (euclidean) on the PCA coordinates: P [n_all, d] float32 (d <= 64),
-// queries are rows [q0, q0 + nq).  One warp per query: lanes stride over the candidates, every lane
-// keeps its own sorted top-k in registers, then the 32 lists are merged through shared memory.
-// scanpy's neighbors (pp/__init__.py:43 -> sc.pp.neighbors, method "umap") is exact below 4096 cells and
-// approximate (pynndescent) above; this is exact at every size.
-constexpr int KNN_MAXK = 32;
-constexpr int KNN_D = 64;
-template <int KK>
-__global__ void __launch_bounds__(128) knn_kernel(const float* __restrict__ P, int64_t n_all, int d, int64_t q0, int64_t nq,
-                                                  int32_t* __restrict__ knn_idx, float* __restrict__ knn_d2) {
-    extern __shared__ __align__(16) unsigned char knn_smem[];
-    float* q_s = reinterpret_cast<float*>(knn_smem);                 // [4 warps][KNN_D]
-    float* md = q_s + 4 * KNN_D;                                       // [4 warps][32 * KK]
-    int32_t* mi = reinterpret_cast<int32_t*>(md + 4 * 32 * KK);        // [4 warps][32 * KK]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t q = (int64_t)blockIdx.x * 4 + w;
-    if (q >= nq) return;
-    const int64_t qi = q0 + q;
-    for (int c = lane; c < KNN_D; c += 32) q_s[w * KNN_D + c] = c < d ? P[qi * d + c] : 0.f;
-    __syncwarp();
-    float bd[KK];
-    int32_t bi[KK];
-#pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        bd[t] = INFINITY;
-        bi[t] = -1;
-    }
-    for (int64_t j = lane; j < n_all; j += 32) {
-        const float* pj = P + j * d;
-        float s = 0.f;
-        for (int c = 0; c < d; ++c) {
-            const float diff = q_s[w * KNN_D + c] - __ldg(pj + c);
-            s = fmaf(diff, diff, s);
-        }
-        if (s < bd[KK - 1] || (s == bd[KK - 1] && (int32_t)j < bi[KK - 1])) {
-            // insertion into the sorted list (ties: smaller index first)
-            float cd = s;
-            int32_t ci = (int32_t)j;
-#pragma unroll
-            for (int t = 0; t < KK; ++t) {
-                const bool before = cd < bd[t] || (cd == bd[t] && ci < bi[t]);
-                const float td = bd[t];
-                const int32_t tix = bi[t];
-                if (before) {
-                    bd[t] = cd;
-                    bi[t] = ci;
-                    cd = td;
-                    ci = tix;
-                }
-            }
-        }
-    }
-    // merge: dump the 32 sorted lists, then KK rounds of "warp-wide minimum of the list heads"
-    float* mdw = md + (size_t)w * 32 * KK;
-    int32_t* miw = mi + (size_t)w * 32 * KK;
-#pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        mdw[lane * KK + t] = bd[t];
-        miw[lane * KK + t] = bi[t];
-    }
-    __syncwarp();
-    int head = 0;
-    for (int t = 0; t < KK; ++t) {
-        float hd = head < KK ? mdw[lane * KK + head] : INFINITY;
-        int32_t hi = head < KK ? miw[lane * KK + head] : 0x7fffffff;
-        float bdv = hd;
-        int32_t biv = hi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bdv, o);
-            const int32_t oi = __shfl_xor_sync(0xffffffffu, biv, o);
-            if (od < bdv || (od == bdv && oi < biv)) {
-                bdv = od;
-                biv = oi;
-            }
-        }
-        if (hd == bdv && hi == biv) ++head;  // exactly one lane owns that (distance, index) pair
-        if (lane == 0) {
-            knn_idx[q * KK + t] = biv;
-            knn_d2[q * KK + t] = bdv;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // umap-learn's fuzzy_simplicial_set pieces for one row each (smooth_knn_dist + membership strengths),
 // restated from the published algorithm (umap-learn 0.5, umap_.py: smooth_knn_dist /
 // compute_membership_strengths; local_connectivity = 1, bandwidth = 1, 64 bisection steps, tolerance 1e-5).
@@ -283,38 +197,102 @@ __global__ void __launch_bounds__(256) fuzzy_rows_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-// Community detection on the symmetric weighted CNV neighbourhood graph (CSR, both directions stored):
-// one synchronous local-moving sweep of modularity optimisation with the RB-configuration null model
-// (gamma * k_i * K_c / 2m), the quality leidenalg maximises for scanpy's tl.leiden.  One thread per node;
-// degrees of this graph are ~15-60 so the per-node neighbour-community table lives in registers/local.
-// A node only moves to a community with a smaller label on gain ties, and only half of the nodes
-// (by parity of a hash of the sweep) are allowed to move per sweep, which keeps the synchronous
-// update from oscillating.
+// Community detection on the symmetric weighted CNV neighbourhood graph (CSR, both directions stored): the Leiden scheme
+// (Traag, Waltman & van Eck 2019 — what leidenalg runs for scanpy's tl.leiden, /root/reference/src/infercnvpy/tl/
+// __init__.py:24-30) with the RB-configuration quality  sum_c [ w_in(c) - gamma * K_c^2 / 2m ]:
+//   1. local moving   nodes move to the neighbouring community with the best gain
+//   2. refinement     inside every community of step 1 ("bound") the nodes start again as singletons; a singleton that is
+//                     well connected to its bound ( w(v, C - v) >= gamma * k_v * (K_C - k_v) / 2m ) may join a
+//                     neighbouring sub-community OF THE SAME BOUND if that has a positive gain -> sub-communities are
+//                     connected by construction
+//   3. aggregation    the sub-communities become the nodes of the next level and start it in their bound's community
+// Both sweeps are synchronous and data-parallel (one thread per node; a CTA with a shared-memory hash table for nodes with
+// more than LV_MAXDEG edges — hubs, and the nodes of aggregated levels).  A hash of (node, sweep) lets only half of the
+// nodes move per sweep, gain ties go to the smaller label, and in the refinement a singleton only joins another singleton
+// with a smaller label: no two nodes can swap, so the synchronous update does not oscillate.  Sums run in a fixed order
+// (thread path) or in 2^-20 fixed point (hash path): the result is run-to-run deterministic.
 constexpr int LV_MAXDEG = 96;
-__global__ void __launch_bounds__(128) louvain_sweep_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                                                            const float* __restrict__ w, const double* __restrict__ kdeg,
-                                                            const int32_t* __restrict__ comm, const double* __restrict__ ctot,
-                                                            int64_t n, double two_m, double gamma, int sweep,
-                                                            int32_t* __restrict__ comm_new, int32_t* __restrict__ n_moved) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int32_t ci = comm[i];
-    comm_new[i] = ci;
-    // checkerboard: hash(i, sweep) parity decides who may move in this sweep
+constexpr int LV_HASH = 8192;       // slots of the heavy path's table (distinct neighbouring communities <= 3/4 of it)
+constexpr double LV_FIX = 1048576.0;  // 2^20
+
+struct SweepArgs {
+    const int64_t* indptr;
+    const int32_t* indices;
+    const float* w;
+    const double* kdeg;
+    const int32_t* comm;    // current assignment (refinement: the sub-community)
+    const int32_t* bound;   // refinement only: community of step 1; nullptr = local moving
+    const double* ctot;     // total degree per community of `comm`
+    const double* btot;     // refinement: total degree per bound
+    const int32_t* csize;   // refinement: members per sub-community
+    int64_t n;
+    double two_m, gamma;
+    int sweep;
+    int32_t* comm_new;
+    int32_t* stats;         // [0] nodes moved, [1] heavy nodes queued, [2] hash overflow flag
+    int32_t* heavy;         // queue of nodes with more than LV_MAXDEG edges
+};
+
+__device__ __forceinline__ bool sweep_active(int64_t i, int sweep) {
     uint32_t h = (uint32_t)i * 2654435761u + (uint32_t)sweep * 40503u;
     h ^= h >> 15;
-    if ((h & 1u) != 0u) return;
-    const int64_t e0 = indptr[i], e1 = indptr[i + 1];
-    const int deg = (int)((e1 - e0) < (int64_t)LV_MAXDEG ? (e1 - e0) : (int64_t)LV_MAXDEG);
+    return (h & 1u) == 0u;
+}
+
+// decision for node i given its aggregated neighbourhood: (cs[t], ws[t]) for t < nc = weight to every other candidate
+// community, w_own = weight to its own community (local moving) / w_bound = weight to its bound without itself (refinement)
+__device__ __forceinline__ int32_t sweep_decide(const SweepArgs& a, int64_t i, int32_t ci, const int32_t* cs, const double* ws, int nc,
+                                                double w_own, double w_bound) {
+    const double ki = a.kdeg[i];
+    double best;
+    int32_t best_c = ci;
+    if (a.bound == nullptr) {
+        best = w_own - a.gamma * ki * (a.ctot[ci] - ki) / a.two_m;  // gain of staying, relative to being isolated
+    } else {
+        const double Kc = a.btot[a.bound[i]];
+        if (w_bound < a.gamma * ki * (Kc - ki) / a.two_m) return ci;  // not well connected to its bound: stays alone
+        best = 1e-12;                                                  // a singleton only moves for a positive gain
+    }
+    for (int t = 0; t < nc; ++t) {
+        const int32_t c = cs[t];
+        if (a.bound != nullptr && a.csize[c] == 1 && c > ci) continue;  // two singletons: only the larger label moves
+        const double g = ws[t] - a.gamma * ki * a.ctot[c] / a.two_m;
+        if (g > best + 1e-12 || (best_c != ci && fabs(g - best) <= 1e-12 && c < best_c)) {
+            best = g;
+            best_c = c;
+        }
+    }
+    return best_c;
+}
+
+__global__ void __launch_bounds__(128) community_sweep_kernel(const SweepArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int32_t ci = a.comm[i];
+    a.comm_new[i] = ci;
+    if (!sweep_active(i, a.sweep)) return;
+    const bool refine = a.bound != nullptr;
+    if (refine && a.csize[ci] != 1) return;  // only singletons move in the refinement
+    const int64_t e0 = a.indptr[i], e1 = a.indptr[i + 1];
+    if (e1 - e0 > LV_MAXDEG) {
+        a.heavy[atomicAdd(a.stats + 1, 1)] = (int32_t)i;
+        return;
+    }
+    const int deg = (int)(e1 - e0);
+    const int32_t bi = refine ? a.bound[i] : 0;
     int32_t cs[LV_MAXDEG];
-    float ws[LV_MAXDEG];
+    double ws[LV_MAXDEG];
     int nc = 0;
-    float w_own = 0.f;
+    double w_own = 0.0, w_bound = 0.0;
     for (int e = 0; e < deg; ++e) {
-        const int32_t j = indices[e0 + e];
+        const int32_t j = a.indices[e0 + e];
         if (j == (int32_t)i) continue;
-        const int32_t cj = comm[j];
-        const float wj = w[e0 + e];
+        const double wj = (double)a.w[e0 + e];
+        if (refine) {
+            if (a.bound[j] != bi) continue;
+            w_bound += wj;
+        }
+        const int32_t cj = a.comm[j];
         if (cj == ci) {
             w_own += wj;
             continue;
@@ -324,32 +302,127 @@ __global__ void __launch_bounds__(128) louvain_sweep_kernel(const int64_t* __res
             if (cs[t] == cj) break;
         if (t == nc) {
             cs[nc] = cj;
-            ws[nc] = 0.f;
+            ws[nc] = 0.0;
             ++nc;
         }
         ws[t] += wj;
     }
-    const double ki = kdeg[i];
-    // gain of staying (relative to being isolated) vs. joining c
-    double best = (double)w_own - gamma * ki * (ctot[ci] - ki) / two_m;
-    int32_t best_c = ci;
-    for (int t = 0; t < nc; ++t) {
-        const double g = (double)ws[t] - gamma * ki * ctot[cs[t]] / two_m;
-        if (g > best + 1e-12 || (fabs(g - best) <= 1e-12 && cs[t] < best_c)) {
-            best = g;
-            best_c = cs[t];
-        }
-    }
+    const int32_t best_c = sweep_decide(a, i, ci, cs, ws, nc, w_own, w_bound);
     if (best_c != ci) {
-        comm_new[i] = best_c;
-        atomicAdd(n_moved, 1);
+        a.comm_new[i] = best_c;
+        atomicAdd(a.stats, 1);
     }
 }
 
-__global__ void louvain_ctot_kernel(const int32_t* __restrict__ comm, const double* __restrict__ kdeg, int64_t n,
-                                    double* __restrict__ ctot) {
+// heavy nodes: one CTA per queued node, neighbouring communities aggregated in a shared-memory hash table (fixed point)
+__global__ void __launch_bounds__(256) community_sweep_heavy_kernel(const SweepArgs a) {
+    extern __shared__ __align__(16) unsigned char lv_smem[];
+    unsigned long long* vals = reinterpret_cast<unsigned long long*>(lv_smem);  // [LV_HASH]
+    int32_t* keys = reinterpret_cast<int32_t*>(vals + LV_HASH);                  // [LV_HASH]
+    __shared__ unsigned long long s_own, s_bound;
+    __shared__ double s_best[256];
+    __shared__ int32_t s_bestc[256];
+    const int n_heavy = a.stats[1];
+    const bool refine = a.bound != nullptr;
+    for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const int64_t i = a.heavy[h];
+        const int32_t ci = a.comm[i];
+        const int32_t bi = refine ? a.bound[i] : 0;
+        for (int t = threadIdx.x; t < LV_HASH; t += 256) {
+            keys[t] = -1;
+            vals[t] = 0ull;
+        }
+        if (threadIdx.x == 0) s_own = s_bound = 0ull;
+        __syncthreads();
+        const int64_t e0 = a.indptr[i], e1 = a.indptr[i + 1];
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += 256) {
+            const int32_t j = a.indices[e];
+            if (j == (int32_t)i) continue;
+            const unsigned long long wj = (unsigned long long)llrint((double)a.w[e] * LV_FIX);
+            if (refine) {
+                if (a.bound[j] != bi) continue;
+                atomicAdd(&s_bound, wj);
+            }
+            const int32_t cj = a.comm[j];
+            if (cj == ci) {
+                atomicAdd(&s_own, wj);
+                continue;
+            }
+            uint32_t slot = ((uint32_t)cj * 2654435761u) >> (32 - 13);  // LV_HASH = 2^13
+            int probes = 0;
+            while (true) {
+                const int32_t prev = atomicCAS(&keys[slot], -1, cj);
+                if (prev == -1 || prev == cj) {
+                    atomicAdd(&vals[slot], wj);
+                    break;
+                }
+                slot = (slot + 1) & (LV_HASH - 1);
+                if (++probes >= LV_HASH) {  // table full: more distinct neighbouring communities than slots
+                    atomicExch(a.stats + 2, 1);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        // every thread scans its share of the table with the same rule as the thread path, then a fixed-order reduction
+        const double ki = a.kdeg[i];
+        double best = -1e300;
+        int32_t best_c = ci;
+        bool allowed = true;
+        if (!refine) {
+            best = (double)s_own / LV_FIX - a.gamma * ki * (a.ctot[ci] - ki) / a.two_m;
+        } else {
+            const double Kc = a.btot[bi];
+            allowed = (double)s_bound / LV_FIX >= a.gamma * ki * (Kc - ki) / a.two_m;
+            best = 1e-12;
+        }
+        const double base = best;
+        for (int t = threadIdx.x; t < LV_HASH && allowed; t += 256) {
+            const int32_t c = keys[t];
+            if (c < 0) continue;
+            if (refine && a.csize[c] == 1 && c > ci) continue;
+            const double g = (double)vals[t] / LV_FIX - a.gamma * ki * a.ctot[c] / a.two_m;
+            if (g > best + 1e-12 || (best_c != ci && fabs(g - best) <= 1e-12 && c < best_c)) {
+                best = g;
+                best_c = c;
+            }
+        }
+        s_best[threadIdx.x] = best;
+        s_bestc[threadIdx.x] = best_c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double gb = base;
+            int32_t cb = ci;
+            for (int t = 0; t < 256; ++t) {
+                const int32_t c = s_bestc[t];
+                if (c == ci) continue;
+                const double g = s_best[t];
+                if (g > gb + 1e-12 || (cb != ci && fabs(g - gb) <= 1e-12 && c < cb)) {
+                    gb = g;
+                    cb = c;
+                }
+            }
+            if (cb != ci) {
+                a.comm_new[i] = cb;
+                atomicAdd(a.stats, 1);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// totals per community: degree sum (ctot) and member count (csize, optional)
+__global__ void community_totals_kernel(const int32_t* __restrict__ comm, const double* __restrict__ kdeg, int64_t n,
+                                        double* __restrict__ ctot, int32_t* __restrict__ csize) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(ctot + comm[i], kdeg[i]);
+    if (i >= n) return;
+    // fixed point so that the totals do not depend on the order of the atomics
+    atomicAdd(reinterpret_cast<unsigned long long*>(ctot) + comm[i], (unsigned long long)llrint(kdeg[i] * LV_FIX));
+    if (csize) atomicAdd(csize + comm[i], 1);
+}
+__global__ void community_totals_finish_kernel(double* __restrict__ ctot, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ctot[i] = (double)reinterpret_cast<unsigned long long*>(ctot)[i] / LV_FIX;
 }
 
 __global__ void weighted_degree_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ w, int64_t n,
@@ -390,31 +463,6 @@ int graph_project(const float* X, int64_t n, int64_t ld, int K, const double* V,
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }
-int graph_knn(const float* P, int64_t n_all, int d, int64_t q0, int64_t nq, int k, int32_t* idx, float* d2, cudaStream_t st) {
-    if (nq == 0) return 0;
-    if (d > KNN_D || k > KNN_MAXK || k < 1) {
-        set_error("icnv_knn_f32: needs d <= 64 and 1 <= k <= 32");
-        return -3;
-    }
-    const unsigned grid = (unsigned)((nq + 3) / 4);
-#define ICNV_KNN(KK)                                                                                   \
-    do {                                                                                               \
-        const size_t smem = 4 * KNN_D * 4 + (size_t)4 * 32 * KK * 8;                                   \
-        ICNV_CUDA(cudaFuncSetAttribute(knn_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        knn_kernel<KK><<<grid, 128, smem, st>>>(P, n_all, d, q0, nq, idx, d2);                         \
-    } while (0)
-    if (k <= 16) {
-        if (k != 16) {
-            // the kernel is instantiated for 16 and 32; smaller k is served by the next size up and truncated by the caller
-        }
-        ICNV_KNN(16);
-    } else {
-        ICNV_KNN(32);
-    }
-#undef ICNV_KNN
-    ICNV_CUDA(cudaGetLastError());
-    return 0;
-}
 int graph_fuzzy_rows(const float* dist, const int32_t* idx, int64_t n, int k, int64_t row0, float mean_all, float* vals, float* sigma,
                      float* rho, cudaStream_t st) {
     if (n == 0) return 0;
@@ -428,15 +476,54 @@ int graph_weighted_degree(const int64_t* indptr, const float* w, int64_t n, doub
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }
-int graph_louvain_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg, const int32_t* comm,
-                        double* ctot, int64_t n, double two_m, double gamma, int sweep, int32_t* comm_new, int32_t* n_moved,
-                        cudaStream_t st) {
-    if (n == 0) return 0;
+static int community_totals(const int32_t* comm, const double* kdeg, int64_t n, double* ctot, int32_t* csize, cudaStream_t st) {
     ICNV_CUDA(cudaMemsetAsync(ctot, 0, sizeof(double) * n, st));
-    louvain_ctot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(comm, kdeg, n, ctot);
-    ICNV_CUDA(cudaMemsetAsync(n_moved, 0, sizeof(int32_t), st));
-    louvain_sweep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(indptr, indices, w, kdeg, comm, ctot, n, two_m, gamma, sweep,
-                                                                      comm_new, n_moved);
+    if (csize) ICNV_CUDA(cudaMemsetAsync(csize, 0, sizeof(int32_t) * n, st));
+    community_totals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(comm, kdeg, n, ctot, csize);
+    community_totals_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctot, n);
+    ICNV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// One synchronous sweep.  bound == nullptr: local moving; else refinement inside `bound`.  work = [ctot n f64 | btot n f64 |
+// csize n i32 | heavy n i32]; stats = int32[3] {moved, heavy nodes, overflow}.
+int graph_community_sweep(const int64_t* indptr, const int32_t* indices, const float* w, const double* kdeg, const int32_t* comm,
+                          const int32_t* bound, int64_t n, double two_m, double gamma, int sweep, void* work, int32_t* comm_new,
+                          int32_t* stats, cudaStream_t st) {
+    if (n == 0) return 0;
+    double* ctot = reinterpret_cast<double*>(work);
+    double* btot = ctot + n;
+    int32_t* csize = reinterpret_cast<int32_t*>(btot + n);
+    int32_t* heavy = csize + n;
+    int rc = community_totals(comm, kdeg, n, ctot, bound ? csize : nullptr, st);
+    if (rc) return rc;
+    if (bound) {
+        rc = community_totals(bound, kdeg, n, btot, nullptr, st);
+        if (rc) return rc;
+    }
+    ICNV_CUDA(cudaMemsetAsync(stats, 0, 3 * sizeof(int32_t), st));
+    SweepArgs a;
+    a.indptr = indptr;
+    a.indices = indices;
+    a.w = w;
+    a.kdeg = kdeg;
+    a.comm = comm;
+    a.bound = bound;
+    a.ctot = ctot;
+    a.btot = btot;
+    a.csize = csize;
+    a.n = n;
+    a.two_m = two_m;
+    a.gamma = gamma;
+    a.sweep = sweep;
+    a.comm_new = comm_new;
+    a.stats = stats;
+    a.heavy = heavy;
+    community_sweep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(a);
+    ICNV_CUDA(cudaGetLastError());
+    constexpr size_t heavy_smem = (size_t)LV_HASH * 12;
+    ICNV_CUDA(cudaFuncSetAttribute(community_sweep_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
+    community_sweep_heavy_kernel<<<(unsigned)std::min<int64_t>(n, 148 * 2), 256, heavy_smem, st>>>(a);
     ICNV_CUDA(cudaGetLastError());
     return 0;
 }

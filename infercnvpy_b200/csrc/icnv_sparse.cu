@@ -10,7 +10,7 @@
 // in icnv_smooth.cu.  HBM traffic per cell: 8 * nnz + 8 (indptr) + the tile-order fp64 row, instead of 4 * G.
 //
 //   per CTA iteration (one cell row, persistent CTAs, 512 threads):
-//     wait   mbarrier of D[cur]                       (z row landed; refill was issued two iterations ago)
+//     wait   mbarrier of D[cur]                       (z row landed; the refill was issued when the buffer died)
 //     S      all warps: entries (col, val) -> table[col] -> d = clip(centre(val)) -> D[cur][slot]
 //     bar A  (CTA)                                    group warps arrive here after P of the previous row
 //     G      all warps: thread per group, 5 x LDS.64 -> A, B (, C') in fp64 -> AB[g]
@@ -84,8 +84,10 @@ __global__ void col_table_kernel(const TR* __restrict__ ref, int n_cat, int G, c
     col_tab[c] = make_int4(col_slot[c], __float_as_int((float)mn), __float_as_int((float)mx), 0);
 }
 
-template <int NWIN, int GS, bool BOUNDED>
-__global__ void __launch_bounds__(NT, 1) smooth_csr_kernel(const SparseParams p) {
+// DBL: two staged rows D[2] and one CTA per SM (windows with a peak group: the third partial sum leaves no room for a
+// second CTA); otherwise one staged row per CTA and TWO CTAs per SM, whose phases interleave.
+template <int NWIN, int GS, bool BOUNDED, bool DBL>
+__global__ void __launch_bounds__(NT, DBL ? 1 : 2) smooth_csr_kernel(const SparseParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NQ_C = NWIN / GS;
     constexpr bool M3_C = (NWIN / 2) % GS != 0;
@@ -93,8 +95,9 @@ __global__ void __launch_bounds__(NT, 1) smooth_csr_kernel(const SparseParams p)
     static_assert(NWIN % 2 == 0 && NWIN % GS == 0 && GS % 2 == 0, "templated even windows, even groups (LDS.64 walks)");
     const int ABS = p.NGpad + PAD_GROUPS;
     SparseScratch* sc = reinterpret_cast<SparseScratch*>(smem);
-    float* D = reinterpret_cast<float*>(smem + 16);                    // [2][DP]
-    double2* AB = reinterpret_cast<double2*>(D + 2 * (size_t)p.DP);     // [ABS]
+    constexpr int NBUF = DBL ? 2 : 1;
+    float* D = reinterpret_cast<float*>(smem + 16);                       // [NBUF][DP]
+    double2* AB = reinterpret_cast<double2*>(D + NBUF * (size_t)p.DP);     // [ABS]
     double* Cp = M3_C ? reinterpret_cast<double*>(AB + ABS) : nullptr;  // [ABS]
 
     // same warp numbering as smooth_kernel: the warps that own outputs take the highest physical ids
@@ -124,10 +127,23 @@ __global__ void __launch_bounds__(NT, 1) smooth_csr_kernel(const SparseParams p)
         for (uint32_t off = 0; off < row_bytes; off += CH)
             bulk_g2s_plain(dst + off, src + off, min(CH, row_bytes - off), &sc->mbar[buf]);
     };
+    // the entries of an upcoming row, pulled into L2 ahead of time (16-byte granules, clamped to the arrays)
+    const int64_t nnz_all = __ldg(p.indptr + p.n_rows);
+    auto prefetch_entries = [&](int64_t r) {
+        const int64_t e0 = __ldg(p.indptr + r) & ~(int64_t)3, e1 = min((__ldg(p.indptr + r + 1) + 3) & ~(int64_t)3, nnz_all & ~(int64_t)3);
+        if (e1 <= e0) return;
+        constexpr int64_t CHE = 4096;  // entries per prefetch instruction (16 KB)
+        for (int64_t e = e0; e < e1; e += CHE) {
+            const uint32_t bytes = (uint32_t)(min(CHE, e1 - e) * 4);
+            bulk_prefetch_l2(p.indices + e, bytes);
+            bulk_prefetch_l2(p.data + e, bytes);
+        }
+    };
     const int64_t first = blockIdx.x;
     if (tid == ISSUER) {
         if (first < p.n_rows) refill(0);
-        if (first + gridDim.x < p.n_rows) refill(1);
+        if (DBL && first + gridDim.x < p.n_rows) refill(1);
+        if (first + gridDim.x < p.n_rows) prefetch_entries(first + gridDim.x);
     }
 
     const int n_group = ((p.n_tasks + 31) >> 5) << 5;
@@ -138,10 +154,10 @@ __global__ void __launch_bounds__(NT, 1) smooth_csr_kernel(const SparseParams p)
 
     int it = 0;
     for (int64_t row = first; row < p.n_rows; row += gridDim.x, ++it) {
-        const int cur = it & 1;
+        const int cur = DBL ? (it & 1) : 0;
         float* Dc = D + (size_t)cur * p.DP;
         // ======================= S: scatter the row's entries over the constant row =======================
-        mbar_wait(&sc->mbar[cur], (uint32_t)((it >> 1) & 1));
+        mbar_wait(&sc->mbar[cur], (uint32_t)((DBL ? (it >> 1) : it) & 1));
         {
             const int64_t e0 = __ldg(p.indptr + row), e1 = __ldg(p.indptr + row + 1);
             int64_t e = e0 + tid;
@@ -198,7 +214,11 @@ __global__ void __launch_bounds__(NT, 1) smooth_csr_kernel(const SparseParams p)
             if (M3_C) Cp[g] = c;
         }
         __syncthreads();  // bar B: partials visible, D[cur] dead
-        if (tid == ISSUER && row + 2 * (int64_t)gridDim.x < p.n_rows) refill(cur);
+        if (tid == ISSUER) {
+            const int64_t nxt = row + (DBL ? 2 : 1) * (int64_t)gridDim.x;  // the row this buffer serves next
+            if (nxt < p.n_rows) refill(cur);
+            if (row + 2 * (int64_t)gridDim.x < p.n_rows) prefetch_entries(row + 2 * (int64_t)gridDim.x);
+        }
         if (!in_group) continue;
 
         // ======================= P: windows (same arithmetic as smooth_kernel, tier 0) =======================
@@ -270,7 +290,7 @@ __global__ void __launch_bounds__(NT, 1) smooth_csr_kernel(const SparseParams p)
 }
 
 size_t sparse_smem_bytes(int DP, int NGpad, bool peak_group) {
-    size_t s = 16 + (size_t)2 * DP * 4 + (size_t)(NGpad + PAD_GROUPS) * 16;
+    size_t s = 16 + (size_t)(peak_group ? 2 : 1) * DP * 4 + (size_t)(NGpad + PAD_GROUPS) * 16;
     if (peak_group) s += (size_t)(NGpad + PAD_GROUPS) * 8;
     return (s + 15) / 16 * 16;
 }
@@ -292,9 +312,17 @@ int sparse_col_table_launch(const void* ref, bool ref_f64, int n_cat, int G, con
 }
 
 template <int NWIN, int GS, bool BOUNDED>
-static int sparse_launch_one(const SparseParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = smooth_csr_kernel<NWIN, GS, BOUNDED>;
+static int sparse_launch_one(const SparseParams& p, int n_sm, size_t smem, cudaStream_t st) {
+    constexpr bool DBL = (NWIN / 2) % GS != 0;
+    auto k = smooth_csr_kernel<NWIN, GS, BOUNDED, DBL>;
     ICNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    ICNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NT, smem));
+    if (occ < 1) {
+        set_error("sparse smoothing kernel does not fit on an SM");
+        return -3;
+    }
+    const int grid = (int)std::min<int64_t>(p.n_rows, (int64_t)n_sm * occ);
     k<<<grid, NT, smem, st>>>(p);
     ICNV_CUDA(cudaGetLastError());
     return 0;
@@ -323,11 +351,10 @@ int sparse_smooth_launch(int nwin, int gs, bool bounded, const int64_t* indptr, 
     p.out = out;
     p.ldo = ldo;
     const size_t smem = sparse_smem_bytes(DP, NGpad, (nwin / 2) % gs != 0);
-    const int grid = (int)std::min<int64_t>(n_rows, n_sm);
     if (nwin == 100 && gs == 10)
-        return bounded ? sparse_launch_one<100, 10, true>(p, grid, smem, st) : sparse_launch_one<100, 10, false>(p, grid, smem, st);
+        return bounded ? sparse_launch_one<100, 10, true>(p, n_sm, smem, st) : sparse_launch_one<100, 10, false>(p, n_sm, smem, st);
     if (nwin == 250 && gs == 10)
-        return bounded ? sparse_launch_one<250, 10, true>(p, grid, smem, st) : sparse_launch_one<250, 10, false>(p, grid, smem, st);
+        return bounded ? sparse_launch_one<250, 10, true>(p, n_sm, smem, st) : sparse_launch_one<250, 10, false>(p, n_sm, smem, st);
     set_error("sparse_smooth_launch: no kernel instantiation for this (window, step)");
     return -3;
 }

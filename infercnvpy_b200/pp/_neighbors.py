@@ -21,20 +21,23 @@ log = logging.getLogger("infercnvpy_b200")
 
 
 def knn_device(P, k: int, q0: int = 0, nq: int | None = None):
-    """Exact euclidean kNN of rows ``[q0, q0+nq)`` of ``P`` (device float32 ``[n, d]``) against all rows.
+    """Exact euclidean kNN of rows ``[q0, q0+nq)`` of ``P`` (device float32 ``[n, d]``, ``d <= 64``) against all rows:
+    tensor-core distance GEMM (tcgen05, 3xTF32) + exact re-rank (``csrc/icnv_knn.cu``).  ``q0`` must be a multiple of 128.
     Returns ``(idx [nq, k] int32, dist [nq, k] float32)``; column 0 is the query itself."""
     import torch
 
     lib = _lib.load()
     n, d = P.shape
     nq = n - q0 if nq is None else nq
-    KK = 16 if k <= 16 else 32
-    idx = torch.empty((nq, KK), dtype=torch.int32, device=P.device)
-    d2 = torch.empty((nq, KK), dtype=torch.float32, device=P.device)
+    assert P.dtype == torch.float32 and P.stride(1) == 1
+    idx = torch.empty((nq, k), dtype=torch.int32, device=P.device)
+    d2 = torch.empty((nq, k), dtype=torch.float32, device=P.device)
+    ws = torch.empty((int(lib.icnv_knn_workspace_bytes(n, nq)),), dtype=torch.uint8, device=P.device)
     _lib.check(
-        lib.icnv_knn_f32(_lib.ptr(P), n, d, q0, nq, k, _lib.ptr(idx), _lib.ptr(d2), _lib.stream_handle(P.device)), "icnv_knn_f32"
+        lib.icnv_knn_f32(_lib.ptr(P), n, d, P.stride(0), q0, nq, k, _lib.ptr(idx), _lib.ptr(d2), k, _lib.ptr(ws), _lib.stream_handle(P.device)),
+        "icnv_knn_f32",
     )
-    return idx[:, :k].contiguous(), d2[:, :k].clamp_min(0).sqrt().contiguous()
+    return idx, d2.clamp_min(0).sqrt()
 
 
 def fuzzy_graph_device(idx, dist, n_total: int, row0: int = 0):
@@ -110,8 +113,8 @@ def neighbors(
     n_neighbors = int(kwargs.pop("n_neighbors", 15))
     P_host = np.ascontiguousarray(np.asarray(adata.obsm[f"X_{use_rep}"]), dtype=np.float32)
     n, d = P_host.shape
-    if not 2 <= n_neighbors <= min(32, n):
-        raise ValueError("n_neighbors must be in [2, min(32, n_obs)]")
+    if not 2 <= n_neighbors <= min(20, n):
+        raise ValueError("n_neighbors must be in [2, min(20, n_obs)]")
     if d > 64:
         raise ValueError("at most 64 dimensions are supported for the neighbour search")
     device = _device()

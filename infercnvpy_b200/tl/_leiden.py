@@ -4,10 +4,11 @@ RBConfigurationVertexPartition, weights, resolution 1, seed 0, until convergence
 
 leidenalg is sequential, randomised and order dependent; label-for-label equality with a parallel implementation is
 not attainable and the reference's tests assert nothing about the clustering: parity unpinned.
-Here: multilevel optimisation of the same quality function (RB-configuration modularity, resolution ``gamma``) —
-synchronous local-moving sweeps on the device (``icnv_louvain_sweep``) + graph aggregation, repeated until no node
-moves at any level.  The Leiden refinement step (guaranteeing well-connected communities) is not implemented yet.
-Labels are strings, numbered by decreasing cluster size like leidenalg's.
+Here: the Leiden scheme on the same quality function (RB-configuration modularity, resolution ``gamma``) — synchronous
+local-moving sweeps, refinement sweeps inside every community (sub-communities are connected by construction) and
+aggregation of the refined partition, all on the device (``icnv_community_sweep``), repeated until a level changes
+nothing.  Deterministic (no random visiting order).  Labels are strings, numbered by decreasing cluster size like
+leidenalg's; the tests compare quality and ARI with a sequential CPU restatement of Leiden (``oracle/leiden_oracle.py``).
 """
 
 from __future__ import annotations
@@ -45,63 +46,100 @@ def modularity_device(indptr, indices, w, labels, gamma: float = 1.0) -> float:
     return float((inside - gamma * (ctot * ctot).sum() / two_m) / two_m)
 
 
-def louvain_device(indptr, indices, w, gamma: float = 1.0, max_levels: int = 20, max_sweeps: int = 200):
-    """Multilevel local moving + aggregation; returns int64 labels (device) numbered arbitrarily."""
+def _sweeps(lib, graph, kdeg, two_m, comm, bound, gamma, work, stats, stream, max_sweeps, sweep0=0):
+    """Synchronous sweeps of ``icnv_community_sweep`` until two consecutive ones (both halves of the checkerboard) move
+    nothing.  Returns ``(assignment, any node moved, sweeps used)``."""
+    import torch
+
+    indptr, indices, w = graph
+    n = indptr.numel() - 1
+    comm_new = torch.empty_like(comm)
+    moved_any, quiet, used = False, 0, 0
+    for sweep in range(max_sweeps):
+        _lib.check(
+            lib.icnv_community_sweep(_lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(w), _lib.ptr(kdeg), _lib.ptr(comm), _lib.ptr(bound),
+                                     n, two_m, float(gamma), sweep0 + sweep, _lib.ptr(work), _lib.ptr(comm_new), _lib.ptr(stats), stream),
+            "icnv_community_sweep",
+        )
+        comm, comm_new = comm_new, comm
+        used += 1
+        m, _, overflow = (int(v) for v in stats.tolist())
+        if overflow:
+            raise _lib.IcnvError("icnv_community_sweep: a node has more distinct neighbouring communities than the hash table holds")
+        if m > 0:
+            moved_any, quiet = True, 0
+        else:
+            quiet += 1
+            if quiet >= 2:
+                break
+    return comm, moved_any, used
+
+
+def leiden_device(indptr, indices, w, gamma: float = 1.0, max_levels: int = 32, max_sweeps: int = 200, refine: bool = True):
+    """Leiden scheme on a symmetric CSR graph (device tensors): local moving, refinement inside every community,
+    aggregation of the refined sub-communities (which start the next level in their community); repeated until a level
+    changes nothing.  ``refine=False`` gives plain multilevel Louvain.  Returns int64 labels (device), numbered arbitrarily."""
     import torch
 
     lib = _lib.load()
     device = w.device
     stream = _lib.stream_handle(device)
     n0 = indptr.numel() - 1
-    labels = torch.arange(n0, device=device, dtype=torch.int64)  # community of every original node
+    node_of = torch.arange(n0, device=device, dtype=torch.int64)   # aggregated node every original node sits in
+    comm = torch.arange(n0, device=device, dtype=torch.int32)       # community of every aggregated node
+    stats = torch.zeros(3, dtype=torch.int32, device=device)
+    sweep0 = 0
     for _level in range(max_levels):
         n = indptr.numel() - 1
+        graph = (indptr, indices, w)
         kdeg = torch.empty(n, dtype=torch.float64, device=device)
         _lib.check(lib.icnv_weighted_degree(_lib.ptr(indptr), _lib.ptr(w), n, _lib.ptr(kdeg), stream), "icnv_weighted_degree")
         two_m = float(kdeg.sum())
         if two_m <= 0:
             break
-        comm = torch.arange(n, device=device, dtype=torch.int32)
-        comm_new = torch.empty_like(comm)
-        ctot = torch.empty(n, dtype=torch.float64, device=device)
-        n_moved = torch.zeros(1, dtype=torch.int32, device=device)
-        moved_any = False
-        quiet = 0
-        for sweep in range(max_sweeps):
-            _lib.check(
-                lib.icnv_louvain_sweep(_lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(w), _lib.ptr(kdeg), _lib.ptr(comm), _lib.ptr(ctot),
-                                       n, two_m, float(gamma), sweep, _lib.ptr(comm_new), _lib.ptr(n_moved), stream),
-                "icnv_louvain_sweep",
-            )
-            comm, comm_new = comm_new, comm
-            m = int(n_moved.item())
-            if m > 0:
-                moved_any = True
-                quiet = 0
-            else:
-                quiet += 1
-                if quiet >= 2:  # both halves of the checkerboard had their turn
-                    break
-        if not moved_any:
-            break
-        # ---- aggregate: relabel communities 0..nc-1 and contract the graph
-        uniq, inv = torch.unique(comm.long(), return_inverse=True)
+        work = torch.empty(int(lib.icnv_community_sweep_work_bytes(n)), dtype=torch.uint8, device=device)
+        # ---- 1. local moving (from the communities inherited from the previous level)
+        comm, moved, used = _sweeps(lib, graph, kdeg, two_m, comm, None, gamma, work, stats, stream, max_sweeps, sweep0)
+        sweep0 += used
+        # ---- 2. refinement: singletons merge inside their community
+        if refine:
+            sub = torch.arange(n, device=device, dtype=torch.int32)
+            sub, _, used = _sweeps(lib, graph, kdeg, two_m, sub, comm, gamma, work, stats, stream, max_sweeps, sweep0)
+            sweep0 += used
+        else:
+            sub = comm
+        uniq, inv = torch.unique(sub.long(), return_inverse=True)
         nc = uniq.numel()
-        labels = inv[labels]
+        if nc == n and not moved:
+            break  # nothing moved and nothing merged: converged
+        # ---- 3. aggregate by sub-community; every new node starts in its members' community
+        first = torch.full((nc,), n, dtype=torch.int64, device=device).scatter_reduce_(0, inv, torch.arange(n, device=device), "amin")
+        new_comm_raw = comm.long()[first]
+        _, new_comm = torch.unique(new_comm_raw, return_inverse=True)
+        node_of = inv[node_of]
         if nc == n:
-            break
+            comm = new_comm.to(torch.int32)
+            if not refine:
+                break
+            continue
         rows = torch.repeat_interleave(torch.arange(n, device=device), (indptr[1:] - indptr[:-1]))
         cr, cc = inv[rows], inv[indices.long()]
         key = cr * nc + cc
         ukey, kinv = torch.unique(key, return_inverse=True)
-        wsum = torch.zeros(ukey.numel(), dtype=torch.float32, device=device).scatter_add_(0, kinv, w)
+        wsum = torch.zeros(ukey.numel(), dtype=torch.float64, device=device).scatter_add_(0, kinv, w.double()).float()
         nr = ukey // nc
         counts = torch.bincount(nr, minlength=nc)
         indptr = torch.zeros(nc + 1, dtype=torch.int64, device=device)
         indptr[1:] = torch.cumsum(counts, 0)
         indices = (ukey % nc).to(torch.int32)
         w = wsum
-    return labels
+        comm = new_comm.to(torch.int32)
+    return comm.long()[node_of]
+
+
+def louvain_device(indptr, indices, w, gamma: float = 1.0, max_levels: int = 32, max_sweeps: int = 200):
+    """Multilevel local moving + aggregation without the refinement step (kept for comparison in the tests)."""
+    return leiden_device(indptr, indices, w, gamma, max_levels, max_sweeps, refine=False)
 
 
 def leiden(
@@ -128,7 +166,7 @@ def leiden(
     A = adata.obsp[ckey]
     device = _device()
     indptr, indices, w = _csr_to_device(sp.csr_matrix(A), device)
-    labels = louvain_device(indptr, indices, w, gamma=resolution)
+    labels = leiden_device(indptr, indices, w, gamma=resolution)
     # number clusters by decreasing size (leidenalg convention)
     counts = torch.bincount(labels)
     order = torch.argsort(counts, descending=True, stable=True)
