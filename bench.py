@@ -221,9 +221,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     names = [args.workload] if args.workload else [w for w in args.workloads.split(",") if w]
     for w in names:
-        if w not in WORKLOADS:
+        if w not in WORKLOADS and w != "graph":
             raise SystemExit(f"unknown workload {w}")
-    head = names[0]
+    head = [w for w in names if w != "graph"][0]
     weak = args.cells is not None
     cells_total = args.cells * world if weak else args.cells_total
 
@@ -400,7 +400,76 @@ def main():
         torch.cuda.empty_cache()
         return res
 
+    def measure_graph():
+        """BASELINE configs[4]: CNV matrix -> PCA(50) -> kNN(15) + fuzzy graph -> Leiden, cells sharded over the ranks
+        (K x K Gram all-reduce, all-gather of the N x 50 coordinates and of the kNN lists; clustering replicated)."""
+        from infercnvpy_b200.pp._neighbors import neighbors_device
+        from infercnvpy_b200.tl._leiden import leiden_device
+        from infercnvpy_b200.tl._pca import pca_device
+
+        K, n_clu = 1792, 12
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)  # same cluster profiles on every rank
+        centers = (torch.rand((n_clu, K), generator=gen, device=dev) < 0.08).float() * torch.randn((n_clu, K), generator=gen, device=dev) * 0.15
+        gen.manual_seed(100 + rank)
+        lab = torch.randint(0, n_clu, (n_local,), generator=gen, device=dev)
+        X = torch.empty((n_local, K), dtype=torch.float32, device=dev)
+        for a in range(0, n_local, 100_000):
+            b = min(n_local, a + 100_000)
+            noise = torch.randn((b - a, K), generator=gen, device=dev) * 0.05
+            noise *= (torch.rand((b - a, K), generator=gen, device=dev) < 0.15)
+            X[a:b] = centers[lab[a:b]] + noise
+        steps_g, warm_g = max(1, min(args.steps, 2)), 1
+        stage = {"pca": [], "neighbors": [], "leiden": []}
+        total = []
+        n_clusters = 0
+        for it in range(warm_g + steps_g):
+            barrier()
+            t0 = time.perf_counter()
+            Y, _, _ = pca_device(X, 50)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            g = neighbors_device(Y, 15)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            r, c, w = g["coo"]
+            n_tot = g["n_total"]
+            order = torch.argsort(r * n_tot + c)
+            indptr = torch.zeros(n_tot + 1, dtype=torch.int64, device=dev)
+            indptr[1:] = torch.cumsum(torch.bincount(r, minlength=n_tot), 0)
+            labels = leiden_device(indptr, c[order].to(torch.int32), w[order])
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            if it >= warm_g:
+                stage["pca"].append(t1 - t0)
+                stage["neighbors"].append(t2 - t1)
+                stage["leiden"].append(t3 - t2)
+                total.append(t3 - t0)
+            n_clusters = int(labels.max().item()) + 1
+        tt = torch.tensor([float(np.mean(total))] + [float(np.mean(stage[k])) for k in ("pca", "neighbors", "leiden")], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt[0])
+        # purity of the recovered clusters on this rank's rows (sanity: the planted structure is found)
+        row0 = g["row0"]
+        mine = labels[row0 : row0 + n_local]
+        joint = torch.zeros((n_clusters, n_clu), dtype=torch.int64, device=dev)
+        joint.index_put_((mine, lab), torch.ones_like(lab), accumulate=True)
+        purity = float(joint.max(dim=1).values.sum()) / max(1, n_local)
+        flops_exec = 2.0 * n_local * cells_total * 56 * 3  # 3xTF32 passes over ceil(50/8)*8 = 56 dims, this rank's queries
+        return {
+            "value": cells_total / sec, "unit": "cells/s", "seconds_per_step": sec, "steps": steps_g, "warmup": warm_g,
+            "stage_seconds": {"pca": float(tt[1]), "neighbors": float(tt[2]), "leiden": float(tt[3])},
+            "clusters": n_clusters, "purity": purity,
+            "config": {"workload": "synthetic CNV matrix (cells x 1792 windows, 12 planted clones) -> PCA(50) + kNN(15) + Leiden (BASELINE configs[4])",
+                       "cells_total": cells_total, "windows": K, "n_comps": 50, "n_neighbors": 15, "sharding": f"rows over {world} rank(s)"},
+            "knn_executed_tflop_per_rank": flops_exec / 1e12,
+        }
+
     results = {}
+    want_graph = "graph" in names
+    names = [w for w in names if w != "graph"]
+    head = names[0]
     dense_names = [w for w in names if WORKLOADS[w][2] == "dense"]
     csr_names = [w for w in names if WORKLOADS[w][2] == "csr"]
     for w in dense_names:
@@ -463,6 +532,7 @@ def main():
                    f"every rank runs its {'whole shard' if n_e2e == n_local else f'first {n_e2e} rows of its shard (host memory bound)'}",
         }
 
+    graph_res = measure_graph() if want_graph else None
     sampler.stop()
     clocks = None
     if rank == 0:
@@ -486,7 +556,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": h["config"], "clocks": clocks, "e2e": e2e, "gpu_launches": h["gpu_launches"],
             "roofline": h["roofline"], "cpu_baseline": cpu_baseline, "impl": "b200",
             "whole_step_frac_of_peak": h["whole_step_frac_of_peak"],
-            "sub": {k: v for k, v in results.items() if k != head},
+            "sub": {**{k: v for k, v in results.items() if k != head}, **({"graph": graph_res} if graph_res else {})},
             "dtype_note": "fp32 input/centring/output, fp64 window accumulation (the reference computes the convolution in float64)",
         }
         print(json.dumps(line))

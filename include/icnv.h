@@ -181,7 +181,7 @@ int icnv_project_f32(const float* X, int64_t n_rows, int64_t ld, int32_t K, cons
                      const double* mu, float* Y, void* stream);
 /* Exact euclidean kNN of rows [q0, q0+nq) of P [n_all, d <= 64] float32 (row pitch ld) against all rows, as a tensor-core
  * distance GEMM (tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM) + exact fp64 re-rank of k + slack candidates
- * per query (csrc/icnv_knn.cu).  k <= 20; q0 must be a multiple of 128.  knn_idx / knn_d2 are [nq, out_ld]: the k nearest
+ * per query (csrc/icnv_knn.cu).  k <= 20.  knn_idx / knn_d2 are [nq, out_ld]: the k nearest
  * by ascending squared distance, ties by index (column 0 is the query itself).  workspace: icnv_knn_workspace_bytes. */
 int64_t icnv_knn_workspace_bytes(int64_t n_all, int64_t nq);
 int icnv_knn_f32(const float* P, int64_t n_all, int32_t d, int64_t ld, int64_t q0, int64_t nq, int32_t k, int32_t* knn_idx,

@@ -933,6 +933,15 @@ int icnv_gene_values(icnv_plan* plan, const double* tmp, int64_t n_rows, int64_t
         gp.v_in_smem = 1;
         smem += (size_t)plan->n_cov * 8;
     }
+    {   // work area of the histogram selection (16 per-warp histograms of 512 bins + 2048 candidates) when it still fits
+        const size_t work = (size_t)16 * 512 * 4 + (size_t)2048 * 8;
+        const size_t at = (smem + 15) / 16 * 16;
+        gp.hist_off = -1;
+        if (at + work <= budget) {
+            gp.hist_off = (int32_t)at;
+            smem = at + work;
+        }
+    }
     const int grid = (int)std::min<int64_t>(n_rows, (int64_t)plan->n_sm);  // 118 registers x 512 threads: one CTA per SM
     if (!gp.v_in_smem) {
         const size_t need = (size_t)grid * std::max(plan->n_cov, 1);

@@ -132,6 +132,7 @@ struct GeneValParams {
     double* out;             // [n_rows, ldo] float64
     int64_t ldo;
     int32_t k_in_smem, v_in_smem;
+    int32_t hist_off;        // byte offset of the histogram-selection work area in dynamic shared memory, -1 = none
 };
 
 // ---------------------------------------------------------------- PTX helpers

@@ -7,8 +7,9 @@
 //   the layer is centred on ITS OWN row median (:444) and filtered with the WINDOW matrix's chunk threshold (:453).
 // One CTA per row (persistent, grid-stride).  The window values (K doubles) and the per-gene means (n_cov doubles) live
 // in shared memory when they fit (bench shape: 14 KB + 160 KB), otherwise the means go to an L2-resident scratch row
-// per CTA and the windows are read through the tile-order address table.  The median is an exact radix selection on the
-// order-preserving 64-bit pattern (8 passes of 8 bits, smem histogram); the final sweep walks the natural gene columns
+// per CTA and the windows are read through the tile-order address table.  The median is exact: a histogram bracket around
+// the row mean + exact ranking of the middle bin (icnv_select.cuh, cta_median_hist) when shared memory has room for its
+// work area, else the radix selection on the order-preserving 64-bit pattern; the final sweep walks the natural gene columns
 // so every store is coalesced (streaming, fp64) — the layer is a dense [n_rows, n_genes] float64 matrix (160 KB per cell
 // at 20k genes), which is what bounds this kernel: 8 * n_genes bytes written per cell.
 #include "icnv_common.cuh"
@@ -81,6 +82,7 @@ __device__ double np_pairwise_sum(F get, int a0, int n) {
 __global__ void __launch_bounds__(GV_NT, 1) gene_values_kernel(const GeneValParams p) {
     extern __shared__ __align__(16) unsigned char gv_smem[];
     __shared__ SelectSmem sel;
+    __shared__ HistSmem hsel;
 
     double* sk = p.k_in_smem ? reinterpret_cast<double*>(gv_smem) : nullptr;
     double* sv = p.v_in_smem ? reinterpret_cast<double*>(gv_smem) + (p.k_in_smem ? p.K : 0)
@@ -108,7 +110,8 @@ __global__ void __launch_bounds__(GV_NT, 1) gene_values_kernel(const GeneValPara
         __syncthreads();  // (global scratch: writes by this CTA are visible to it after the barrier)
 
         // ---- exact np.median of the covered genes (:444)
-        const double m = cta_median<GV_NT>([&](int i) { return sv[i]; }, n, sel);
+        const double m = p.hist_off >= 0 ? cta_median_hist<GV_NT>([&](int i) { return sv[i]; }, n, sel, hsel, gv_smem + p.hist_off)
+                                         : cta_median<GV_NT>([&](int i) { return sv[i]; }, n, sel);
 
         // ---- centre, filter, natural-order write
         const double t = p.thr ? p.thr[row / p.chunk_rows] : -1.0;

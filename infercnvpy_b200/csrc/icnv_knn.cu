@@ -43,7 +43,7 @@ constexpr int KNN_THREADS = 192;
 
 // ------------------------------------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(256) knn_pack_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ld, int64_t n_pad,
-                                                       float* __restrict__ packed, float* __restrict__ norms) {
+                                                       float* __restrict__ packed, float* __restrict__ norms /* nullable */) {
     // thread = (point, k chunk): 16 threads per point read 4 consecutive floats each
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t pt = gid / KNN_CHUNKS;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) knn_pack_kernel(const float* __restrict__
     // |x|^2: sum over the 16 chunk threads of a point (they are consecutive lanes of one half-warp)
 #pragma unroll
     for (int sh = 8; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
-    if (ch == 0) norms[pt] = pt < n ? (float)s : INFINITY;
+    if (ch == 0 && norms != nullptr) norms[pt] = pt < n ? (float)s : INFINITY;
 }
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -117,6 +117,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Rare path of the epilogue, kept out of line: 128 inlined copies per tile made the kernel 4800 instructions long and the
+// epilogue warps stalled on instruction fetch ("no_inst" on every reconvergence point, ncu r2).  Everything it changes
+// lives in shared memory and the new bar comes back BY VALUE: reference parameters put `thr` on the stack and every
+// compare of the hot loop then waited for a local-memory load.
+//   lmeta[row] = entries in the list (<= KK) | position of the worst entry << 8
+__device__ __noinline__ float knn_insert(float* lkey, int32_t* lidx, int32_t* lmeta, int row, float key, int32_t id) {
+    const int meta = lmeta[row];
+    int cnt = meta & 0xFF;
+    const int slot = cnt < KNN_KK ? cnt : (meta >> 8);
+    lkey[slot * KNN_TILE + row] = key;
+    lidx[slot * KNN_TILE + row] = id;
+    if (cnt < KNN_KK) ++cnt;
+    float thr = INFINITY;
+    int maxpos = 0;
+    if (cnt == KNN_KK) {  // (re)locate the worst entry: it is the bar the next candidates must pass
+        float v[KNN_KK];
+#pragma unroll
+        for (int i = 0; i < KNN_KK; ++i) v[i] = lkey[i * KNN_TILE + row];
+        float m = v[0];
+#pragma unroll
+        for (int i = 1; i < KNN_KK; ++i)
+            if (v[i] > m) {
+                m = v[i];
+                maxpos = i;
+            }
+        thr = m;
+    }
+    lmeta[row] = cnt | (maxpos << 8);
+    return thr;
+}
+
 struct __align__(16) KnnSmem {
     unsigned long long full[KNN_STAGES], empty[KNN_STAGES], tmem_full[2], tmem_empty[2], a_full;
     uint32_t tmem_base;
@@ -124,18 +155,22 @@ struct __align__(16) KnnSmem {
 };
 
 // ------------------------------------------------------------------------------------------------ main kernel
-__global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __restrict__ packed, const float* __restrict__ norms,
-                                                                 int64_t n_cand_tiles, int64_t q_tile0, int n_ksteps,
+__global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __restrict__ packed, const float* __restrict__ packed_q,
+                                                                 const float* __restrict__ norms, int64_t n_cand_tiles, int n_ksteps,
                                                                  int32_t* __restrict__ cand_idx /* [n_q_tiles*128, KK] */) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    // layout: [A hi|lo 64 KB][B stage 0 64 KB][B stage 1 64 KB][lists key KK*128*4][lists idx KK*128*4][KnnSmem]
+    // layout: [A hi|lo 64 KB][B stage 0 64 KB][B stage 1 64 KB][lists key KK*128*4][lists idx KK*128*4][norms 4 x 128][meta 128][KnnSmem]
     unsigned char* sA = smem;
     unsigned char* sB = smem + KNN_BLOCK_BYTES;
     float* lkey = reinterpret_cast<float*>(smem + (size_t)(1 + KNN_STAGES) * KNN_BLOCK_BYTES);
     int32_t* lidx = reinterpret_cast<int32_t*>(lkey + KNN_KK * KNN_TILE);
-    KnnSmem* S = reinterpret_cast<KnnSmem*>(lidx + KNN_KK * KNN_TILE);
+    // |c|^2 of the candidate tiles in flight: a ring of 4 (2 stages + 2 accumulators: tile t + 2 is only loaded after the
+    // MMAs of tile t, which wait for the epilogue of tile t - 2, so slots t - 1, t, t + 1 are never overwritten)
+    float* cnorm = reinterpret_cast<float*>(lidx + KNN_KK * KNN_TILE);
+    int32_t* lmeta = reinterpret_cast<int32_t*>(cnorm + 4 * KNN_TILE);
+    KnnSmem* S = reinterpret_cast<KnnSmem*>(lmeta + KNN_TILE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t q_tile = q_tile0 + blockIdx.x;
+    const int64_t q_tile = blockIdx.x;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < KNN_STAGES; ++s) {
@@ -163,13 +198,14 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __
         if (lane == 0) {
             constexpr uint32_t CH = 16384;
             mbar_expect_tx(&S->a_full, KNN_BLOCK_BYTES);
-            const char* srcA = reinterpret_cast<const char*>(packed) + (size_t)q_tile * KNN_BLOCK_BYTES;
+            const char* srcA = reinterpret_cast<const char*>(packed_q) + (size_t)q_tile * KNN_BLOCK_BYTES;
             for (uint32_t off = 0; off < KNN_BLOCK_BYTES; off += CH) bulk_g2s_plain(sA + off, srcA + off, CH, &S->a_full);
             for (int64_t t = 0; t < n_cand_tiles; ++t) {
                 const int s = (int)(t % KNN_STAGES);
                 const uint32_t use = (uint32_t)(t / KNN_STAGES);
                 if (use > 0) mbar_wait(&S->empty[s], (use - 1) & 1u);
-                mbar_expect_tx(&S->full[s], KNN_BLOCK_BYTES);
+                mbar_expect_tx(&S->full[s], KNN_BLOCK_BYTES + KNN_TILE * 4);
+                bulk_g2s_plain(cnorm + (t & 3) * KNN_TILE, norms + t * KNN_TILE, KNN_TILE * 4, &S->full[s]);
                 const char* src = reinterpret_cast<const char*>(packed) + (size_t)t * KNN_BLOCK_BYTES;
                 unsigned char* dst = sB + (size_t)s * KNN_BLOCK_BYTES;
                 for (uint32_t off = 0; off < KNN_BLOCK_BYTES; off += CH) bulk_g2s_plain(dst + off, src + off, CH, &S->full[s]);
@@ -212,46 +248,25 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __
         const int quarter = warp & 3;             // the TMEM lanes this warp may touch: 32 * (warp % 4) ..
         const int row = quarter * 32 + lane;      // query row inside the tile
         float thr = INFINITY;                     // current worst key of a full list
-        int cnt = 0, maxpos = 0;
+        lmeta[row] = 0;
         for (int i = 0; i < KNN_KK; ++i) lidx[i * KNN_TILE + row] = -1;
         for (int64_t t = 0; t < n_cand_tiles; ++t) {
             const int b = (int)(t & 1);
             mbar_wait(&S->tmem_full[b], (uint32_t)(t >> 1) & 1u);
             tc_fence_after();
-            const float* cn = norms + t * KNN_TILE;
+            const float* cn = cnorm + (t & 3) * KNN_TILE;  // landed before the MMAs that filled this accumulator were issued
 #pragma unroll 1
             for (int c0 = 0; c0 < KNN_TILE; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * KNN_TILE + c0), r);
 #pragma unroll
                 for (int j4 = 0; j4 < 32; j4 += 4) {
-                    const float4 n4 = __ldg(reinterpret_cast<const float4*>(cn + c0 + j4));
+                    const float4 n4 = *reinterpret_cast<const float4*>(cn + c0 + j4);
                     const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float key = fmaf(-2.f, __uint_as_float(r[j4 + u]), nn[u]);
-                        if (key < thr) {
-                            const int32_t id = (int32_t)(t * KNN_TILE + c0 + j4 + u);
-                            if (cnt < KNN_KK) {
-                                lkey[cnt * KNN_TILE + row] = key;
-                                lidx[cnt * KNN_TILE + row] = id;
-                                ++cnt;
-                            } else {
-                                lkey[maxpos * KNN_TILE + row] = key;
-                                lidx[maxpos * KNN_TILE + row] = id;
-                            }
-                            if (cnt == KNN_KK) {  // (re)locate the worst entry: it is the bar the next candidates must pass
-                                float m = -INFINITY;
-                                for (int i = 0; i < KNN_KK; ++i) {
-                                    const float v = lkey[i * KNN_TILE + row];
-                                    if (v > m) {
-                                        m = v;
-                                        maxpos = i;
-                                    }
-                                }
-                                thr = m;
-                            }
-                        }
+                        if (key < thr) thr = knn_insert(lkey, lidx, lmeta, row, key, (int32_t)(t * KNN_TILE + c0 + j4 + u));
                     }
                 }
             }
@@ -313,12 +328,12 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-size_t knn_smem_bytes() { return (size_t)(1 + KNN_STAGES) * KNN_BLOCK_BYTES + (size_t)2 * KNN_KK * KNN_TILE * 4 + sizeof(KnnSmem) + 1024; }
+size_t knn_smem_bytes() { return (size_t)(1 + KNN_STAGES) * KNN_BLOCK_BYTES + (size_t)2 * KNN_KK * KNN_TILE * 4 + 5 * KNN_TILE * 4 + sizeof(KnnSmem) + 1024; }
 
 size_t knn_workspace_bytes(int64_t n_all, int64_t nq) {
     const int64_t n_tiles = (n_all + KNN_TILE - 1) / KNN_TILE;
-    const int64_t q_tiles = (nq + KNN_TILE - 1) / KNN_TILE + 1;
-    return (size_t)n_tiles * KNN_BLOCK_BYTES + (size_t)n_tiles * KNN_TILE * 4 + (size_t)q_tiles * KNN_TILE * KNN_KK * 4 + 4096;
+    const int64_t q_tiles = (nq + KNN_TILE - 1) / KNN_TILE;
+    return (size_t)(n_tiles + q_tiles) * KNN_BLOCK_BYTES + (size_t)n_tiles * KNN_TILE * 4 + (size_t)q_tiles * KNN_TILE * KNN_KK * 4 + 4096;
 }
 
 int knn_launch(const float* P, int64_t n_all, int d, int64_t ld, int64_t q0, int64_t nq, int k, int out_ld, int32_t* knn_idx, float* knn_d2,
@@ -331,26 +346,26 @@ int knn_launch(const float* P, int64_t n_all, int d, int64_t ld, int64_t q0, int
         set_error("icnv_knn_f32: k too large for the candidate lists (k <= 20)");
         return -3;
     }
-    if (q0 % KNN_TILE != 0) {
-        set_error("icnv_knn_f32: the first query row must be a multiple of 128");
-        return -2;
-    }
     if (nq == 0) return 0;
     const int64_t n_tiles = (n_all + KNN_TILE - 1) / KNN_TILE;
     const int64_t n_pad = n_tiles * KNN_TILE;
     char* ws = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
-    float* packed = reinterpret_cast<float*>(ws);
-    float* norms = reinterpret_cast<float*>(ws + (size_t)n_tiles * KNN_BLOCK_BYTES);
-    int32_t* cand = reinterpret_cast<int32_t*>(ws + (size_t)n_tiles * KNN_BLOCK_BYTES + (size_t)n_tiles * KNN_TILE * 4);
+    const int64_t q_tiles = (nq + KNN_TILE - 1) / KNN_TILE;
+    float* packed = reinterpret_cast<float*>(ws);                                        // candidates: every point
+    float* packed_q = reinterpret_cast<float*>(ws + (size_t)n_tiles * KNN_BLOCK_BYTES);  // queries: rows q0 .. q0 + nq
+    float* norms = reinterpret_cast<float*>(ws + (size_t)(n_tiles + q_tiles) * KNN_BLOCK_BYTES);
+    int32_t* cand = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(norms) + (size_t)n_tiles * KNN_TILE * 4);
     {
         const int64_t threads = n_pad * KNN_CHUNKS;
         knn_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P, n_all, d, ld, n_pad, packed, norms);
         ICNV_CUDA(cudaGetLastError());
+        const int64_t threads_q = q_tiles * KNN_TILE * KNN_CHUNKS;
+        knn_pack_kernel<<<(unsigned)((threads_q + 255) / 256), 256, 0, st>>>(P + q0 * ld, nq, d, ld, q_tiles * KNN_TILE, packed_q, nullptr);
+        ICNV_CUDA(cudaGetLastError());
     }
-    const int64_t q_tiles = (nq + KNN_TILE - 1) / KNN_TILE;
     const size_t smem = knn_smem_bytes();
     ICNV_CUDA(cudaFuncSetAttribute(knn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_mma_kernel<<<(unsigned)q_tiles, KNN_THREADS, smem, st>>>(packed, norms, n_tiles, q0 / KNN_TILE, (d + 7) / 8, cand);
+    knn_mma_kernel<<<(unsigned)q_tiles, KNN_THREADS, smem, st>>>(packed, packed_q, norms, n_tiles, (d + 7) / 8, cand);
     ICNV_CUDA(cudaGetLastError());
     knn_rerank_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(P, n_all, d, ld, q0, nq, cand, k, out_ld, knn_idx, knn_d2);
     ICNV_CUDA(cudaGetLastError());

@@ -108,4 +108,128 @@ __device__ double cta_median(F get, int n, SelectSmem& ss) {
     return (v1 + v2) / 2.0;
 }
 
+
+// Faster exact median for rows whose values cluster around their mean (the per-gene layer): one pass for the moments, one
+// pass into per-warp histograms of HB uniform bins over mean +- 4 sigma (per-warp copies: the central bins hold ~1 % of the
+// values each, a single shared histogram would serialise on them), then the few values of the bin(s) holding the two
+// middle ranks are collected and ranked exactly.  Falls back to the radix selection above whenever the shortcut does not
+// apply (tiny / constant rows, a middle rank in a clamp bin, too many values in the middle bins).  Same result as
+// cta_median: both return np.median of the values.
+constexpr int SEL_HB = 512;     // histogram bins
+constexpr int SEL_CAP = 2048;   // candidates ranked exactly
+struct HistSmem {
+    double sum[32], sq[32];
+    double lo, inv_w, v1, v2;
+    int b1, b2, below, n_cand, ok;
+};
+// work: int[NTHREADS / 32][SEL_HB] per-warp histograms followed by double[SEL_CAP] candidates
+template <int NTHREADS, typename F>
+__device__ double cta_median_hist(F get, int n, SelectSmem& ss, HistSmem& hs, unsigned char* work) {
+    constexpr int NWARPS = NTHREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n < 4 * SEL_HB) return cta_median<NTHREADS>(get, n, ss);
+    int* whist = reinterpret_cast<int*>(work);
+    double* cand = reinterpret_cast<double*>(work + (size_t)NWARPS * SEL_HB * sizeof(int));
+    // ---- moments
+    double s = 0.0, q = 0.0;
+    for (int i = tid; i < n; i += NTHREADS) {
+        const double x = get(i);
+        s += x;
+        q = fma(x, x, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+        hs.sum[warp] = s;
+        hs.sq[warp] = q;
+    }
+    for (int i = tid; i < NWARPS * SEL_HB; i += NTHREADS) whist[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double S = 0.0, Q = 0.0;
+        for (int w = 0; w < NWARPS; ++w) {
+            S += hs.sum[w];
+            Q += hs.sq[w];
+        }
+        const double mean = S / n, var = Q / n - mean * mean;
+        const double sd = var > 0.0 ? sqrt(var) : 0.0;
+        hs.ok = (sd > 0.0 && isfinite(sd)) ? 1 : 0;
+        hs.lo = mean - 4.0 * sd;
+        hs.inv_w = hs.ok ? (double)SEL_HB / (8.0 * sd) : 0.0;
+        hs.n_cand = 0;
+    }
+    __syncthreads();
+    if (!hs.ok) return cta_median<NTHREADS>(get, n, ss);
+    const double lo = hs.lo, inv_w = hs.inv_w;
+    auto bin_of = [&](double x) {
+        const double t = (x - lo) * inv_w;
+        return t < 0.0 ? 0 : (t >= (double)(SEL_HB - 1) ? SEL_HB - 1 : (int)t);
+    };
+    for (int i = tid; i < n; i += NTHREADS) atomicAdd(&whist[warp * SEL_HB + bin_of(get(i))], 1);
+    __syncthreads();
+    for (int b = tid; b < SEL_HB; b += NTHREADS) {
+        int t = 0;
+        for (int w = 0; w < NWARPS; ++w) t += whist[w * SEL_HB + b];
+        whist[b] = t;  // row 0 now holds the totals (each thread only touches its own columns)
+    }
+    __syncthreads();
+    if (tid < 32) {
+        constexpr int PER = SEL_HB / 32;
+        int c[PER], tot = 0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            c[j] = whist[lane * PER + j];
+            tot += c[j];
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int r1 = (n - 1) >> 1, r2 = n >> 1;
+        int below = incl - tot;
+        for (int j = 0; j < PER; ++j) {
+            if (r1 >= below && r1 < below + c[j]) {
+                hs.b1 = lane * PER + j;
+                hs.below = below;
+            }
+            if (r2 >= below && r2 < below + c[j]) hs.b2 = lane * PER + j;
+            below += c[j];
+        }
+    }
+    __syncthreads();
+    const int b1 = hs.b1, b2 = hs.b2;
+    int m = 0;
+    for (int b = b1; b <= b2; ++b) m += whist[b];
+    if (b1 == 0 || b2 == SEL_HB - 1 || m > SEL_CAP) {
+        __syncthreads();
+        return cta_median<NTHREADS>(get, n, ss);
+    }
+    for (int i = tid; i < n; i += NTHREADS) {
+        const double x = get(i);
+        const int b = bin_of(x);
+        if (b >= b1 && b <= b2) cand[atomicAdd(&hs.n_cand, 1)] = x;
+    }
+    __syncthreads();
+    const int k1 = ((n - 1) >> 1) - hs.below, k2 = (n >> 1) - hs.below;
+    for (int i = tid; i < m; i += NTHREADS) {
+        const double x = cand[i];
+        int less = 0;
+        for (int j = 0; j < m; ++j) {
+            const double y = cand[j];
+            less += (y < x || (y == x && j < i)) ? 1 : 0;
+        }
+        if (less == k1) hs.v1 = x;
+        if (less == k2) hs.v2 = x;
+    }
+    __syncthreads();
+    const double res = (hs.v1 + hs.v2) / 2.0;
+    __syncthreads();  // hs / work may be reused by the next call
+    return res;
+}
+
 }  // namespace icnv

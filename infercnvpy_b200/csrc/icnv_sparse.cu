@@ -159,29 +159,62 @@ __global__ void __launch_bounds__(NT, DBL ? 1 : 2) smooth_csr_kernel(const Spars
         // ======================= S: scatter the row's entries over the constant row =======================
         mbar_wait(&sc->mbar[cur], (uint32_t)((DBL ? (it >> 1) : it) & 1));
         {
-            const int64_t e0 = __ldg(p.indptr + row), e1 = __ldg(p.indptr + row + 1);
-            int64_t e = e0 + tid;
-            constexpr int U = 4;  // entries in flight per thread
-            for (; e + (int64_t)(U - 1) * NT < e1; e += (int64_t)U * NT) {
+            const int64_t e0 = __ldg(p.indptr + row);
+            const int nnz = (int)(__ldg(p.indptr + row + 1) - e0);
+            const int32_t* ip = p.indices + e0;
+            const float* vp = p.data + e0;
+            constexpr int U = 8;  // entries in flight per thread: the phase is two dependent L2 round trips per entry
+            int e = tid;
+            for (; e + (U - 1) * NT < nnz; e += U * NT) {
                 int c[U];
                 float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    c[u] = __ldg(ip + e + u * NT);
+                    v[u] = ldg_stream_f32(vp + e + u * NT);
+                }
+                if constexpr (BOUNDED) {
+                    int4 t[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) t[u] = __ldg(p.col_tab + c[u]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (t[u].x >= 0) Dc[t[u].x] = centre_clip(v[u], __int_as_float(t[u].y), __int_as_float(t[u].z), clipf, true);
+                } else {
+                    int2 t[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) t[u] = __ldg(reinterpret_cast<const int2*>(p.col_tab + c[u]));
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (t[u].x >= 0) Dc[t[u].x] = centre_clip(v[u], __int_as_float(t[u].y), 0.f, clipf, false);
+                }
+            }
+            {   // tail: up to U - 1 entries per thread, still issued together
+                int c[U];
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool ok = e + u * NT < nnz;
+                    c[u] = ok ? __ldg(ip + e + u * NT) : -1;
+                    v[u] = ok ? ldg_stream_f32(vp + e + u * NT) : 0.f;
+                }
                 int4 t[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    c[u] = __ldg(p.indices + e + (int64_t)u * NT);
-                    v[u] = ldg_stream_f32(p.data + e + (int64_t)u * NT);
+                    t[u] = make_int4(-1, 0, 0, 0);
+                    if (c[u] >= 0) {
+                        if constexpr (BOUNDED) {
+                            t[u] = __ldg(p.col_tab + c[u]);
+                        } else {
+                            const int2 t2 = __ldg(reinterpret_cast<const int2*>(p.col_tab + c[u]));
+                            t[u].x = t2.x;
+                            t[u].y = t2.y;
+                        }
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u) t[u] = __ldg(p.col_tab + c[u]);
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (t[u].x >= 0) Dc[t[u].x] = centre_clip(v[u], __int_as_float(t[u].y), __int_as_float(t[u].z), clipf, BOUNDED);
-            }
-            for (; e < e1; e += NT) {
-                const int c = __ldg(p.indices + e);
-                const float v = ldg_stream_f32(p.data + e);
-                const int4 t = __ldg(p.col_tab + c);
-                if (t.x >= 0) Dc[t.x] = centre_clip(v, __int_as_float(t.y), __int_as_float(t.z), clipf, BOUNDED);
             }
         }
         __syncthreads();  // bar A: row complete in D[cur]; the previous row's windows have been read

@@ -22,7 +22,7 @@ log = logging.getLogger("infercnvpy_b200")
 
 def knn_device(P, k: int, q0: int = 0, nq: int | None = None):
     """Exact euclidean kNN of rows ``[q0, q0+nq)`` of ``P`` (device float32 ``[n, d]``, ``d <= 64``) against all rows:
-    tensor-core distance GEMM (tcgen05, 3xTF32) + exact re-rank (``csrc/icnv_knn.cu``).  ``q0`` must be a multiple of 128.
+    tensor-core distance GEMM (tcgen05, 3xTF32) + exact re-rank (``csrc/icnv_knn.cu``).
     Returns ``(idx [nq, k] int32, dist [nq, k] float32)``; column 0 is the query itself."""
     import torch
 
@@ -89,6 +89,59 @@ def symmetrize(rows, cols, vals, n_total: int):
     return r, c, w
 
 
+def allgather_rows(t):
+    """Concatenate the row shards ``t`` (``[n_local, ...]``, same trailing shape on every rank) of all ranks in rank order.
+    Returns ``(full, row0)`` with ``row0`` the global index of this rank's first row.  Identity without a process group.
+    NCCL gathers padded device blocks over NVLink; a gloo group (CPU tests) goes through host tensors."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t, 0
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nccl = dist.get_backend() == "nccl"
+    dev = t.device if nccl else torch.device("cpu")
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.int64, device=dev))
+    sizes = [int(x.item()) for x in sizes]
+    n_max = max(sizes)
+    src = t if nccl else t.cpu()
+    pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    pad[: t.shape[0]] = src
+    blocks = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(blocks, pad)
+    full = torch.cat([b[:n] for b, n in zip(blocks, sizes)], dim=0).to(t.device)
+    return full, sum(sizes[:rank])
+
+
+def neighbors_device(P_local, n_neighbors: int):
+    """kNN + fuzzy graph for this rank's rows of the PCA coordinates (device float32 ``[n_local, d]``).  Under an
+    initialised process group the coordinates of all ranks are all-gathered (N x d floats: 200 MB at 1M cells x 50), every
+    rank searches the neighbours of ITS rows among all N points, and the directed kNN lists are all-gathered again so that
+    every rank holds the whole symmetric graph (<= 2 k N edges) for the clustering.
+    Returns ``dict(idx, dist`` (local rows, global ids)``, row0, n_total, coo=(rows, cols, vals))``."""
+    P_all, row0 = allgather_rows(P_local.contiguous())
+    n_total, n_local = P_all.shape[0], P_local.shape[0]
+    idx, dist = knn_device(P_all, n_neighbors, q0=row0, nq=n_local)
+    rows, cols, vals = fuzzy_graph_device(idx, dist, n_total, row0=row0)
+    rows_all, _ = allgather_rows(rows)
+    cols_all, _ = allgather_rows(cols)
+    vals_all, _ = allgather_rows(vals)
+    r, c, w = symmetrize(rows_all, cols_all, vals_all, n_total)
+    return dict(idx=idx, dist=dist, row0=row0, n_total=n_total, coo=(r, c, w))
+
+
+def _unsupported_kwargs(fn: str, kwargs: dict, accepted: dict):
+    """The reference wrappers forward ``**kwargs`` to scanpy; here only the listed values are implemented.  Anything else
+    would silently give a different result than the caller asked for -> TypeError."""
+    for key, val in kwargs.items():
+        if key not in accepted:
+            raise TypeError(f"{fn}() got an unsupported keyword argument {key!r} (supported: {sorted(accepted)})")
+        ok = accepted[key]
+        if ok is not None and val not in ok:
+            raise TypeError(f"{fn}(): {key}={val!r} is not supported (supported: {ok})")
+
+
 def neighbors(
     adata,
     use_rep: str = "cnv_pca",
@@ -100,8 +153,10 @@ def neighbors(
 
     Same parameters and keys as the reference (``pp/__init__.py:8-43``): distances in
     ``.obsp[key_added + "_distances"]``, connectivities in ``.obsp[key_added + "_connectivities"]``, parameters in
-    ``.uns[key_added]``.  ``n_neighbors`` (default 15, counts the cell itself like scanpy) may be passed as keyword.
-    With ``inplace=False`` the two matrices are returned instead.
+    ``.uns[key_added]``.  ``n_neighbors`` (default 15, counts the cell itself like scanpy) may be passed as keyword; other
+    scanpy keywords are accepted only with the values implemented here (euclidean, method "umap") and raise ``TypeError``
+    otherwise.  With ``inplace=False`` the two matrices are returned instead.  Under an initialised ``torch.distributed``
+    group every rank passes its row shard and receives ITS rows of the global matrices (``[n_local, n_total]``).
     """
     import torch
 
@@ -111,22 +166,29 @@ def neighbors(
         log.warning("X_cnv_pca not found in adata.obsm. Computing PCA with default parameters")
         pca(adata)
     n_neighbors = int(kwargs.pop("n_neighbors", 15))
+    _unsupported_kwargs("neighbors", kwargs, {"metric": ("euclidean",), "method": ("umap",), "knn": (True,), "n_pcs": (None,),
+                                              "random_state": None, "transformer": (None,), "copy": (False,)})
     P_host = np.ascontiguousarray(np.asarray(adata.obsm[f"X_{use_rep}"]), dtype=np.float32)
     n, d = P_host.shape
-    if not 2 <= n_neighbors <= min(20, n):
-        raise ValueError("n_neighbors must be in [2, min(20, n_obs)]")
     if d > 64:
         raise ValueError("at most 64 dimensions are supported for the neighbour search")
     device = _device()
-    P = torch.from_numpy(P_host).to(device)
-    idx, dist = knn_device(P, n_neighbors)
-    rows, cols, vals = fuzzy_graph_device(idx, dist, n)
-    r, c, w = symmetrize(rows, cols, vals, n)
-    conn = sp.csr_matrix((w.cpu().numpy(), (r.cpu().numpy(), c.cpu().numpy())), shape=(n, n), dtype=np.float32)
+    if not 2 <= n_neighbors <= 20:
+        raise ValueError("n_neighbors must be in [2, min(20, n_obs)]")
+    g = neighbors_device(torch.from_numpy(P_host).to(device), n_neighbors)
+    if n_neighbors > g["n_total"]:
+        raise ValueError("n_neighbors must be in [2, min(20, n_obs)]")
+    idx, dist, row0, n_total = g["idx"], g["dist"], g["row0"], g["n_total"]
+    r, c, w = g["coo"]
+    # this rank's rows of the (global) symmetric connectivity matrix: [n, n_total] (square when there is one rank)
+    mine = (r >= row0) & (r < row0 + n)
+    conn = sp.csr_matrix(
+        (w[mine].cpu().numpy(), ((r[mine] - row0).cpu().numpy(), c[mine].cpu().numpy())), shape=(n, n_total), dtype=np.float32
+    )
     # distances: the n_neighbors - 1 true neighbours of every cell (scanpy drops the cell itself)
     ii = np.repeat(np.arange(n), n_neighbors - 1)
     distances = sp.csr_matrix(
-        (dist[:, 1:].reshape(-1).cpu().numpy().astype(np.float64), (ii, idx[:, 1:].reshape(-1).cpu().numpy())), shape=(n, n)
+        (dist[:, 1:].reshape(-1).cpu().numpy().astype(np.float64), (ii, idx[:, 1:].reshape(-1).cpu().numpy())), shape=(n, n_total)
     )
     if inplace:
         adata.obsp[f"{key_added}_distances"] = distances
@@ -136,5 +198,7 @@ def neighbors(
             "distances_key": f"{key_added}_distances",
             "params": {"n_neighbors": n_neighbors, "method": "umap", "metric": "euclidean", "use_rep": f"X_{use_rep}"},
         }
+        if n_total != n:
+            adata.uns[key_added]["shard"] = {"row0": int(row0), "n_total": int(n_total)}
     else:
         return distances, conn

@@ -174,17 +174,26 @@ def _to_host(t):
     torch.cuda.current_stream(t.device).synchronize()
     src = view.numpy()
     out = np.empty(n, dtype=src.dtype)
-    # first touch of a fresh host array is page-fault bound (~5 GB/s per thread): spread it over a few threads
-    step = max(1 << 20, -(-n // 8))
+    # first touch of a fresh host array is page-fault bound (~5 GB/s per thread): spread it over a few threads — the
+    # host cores are shared by all ranks of the box (one process per GPU), so each rank takes its share of them
+    n_thr = _copy_threads()
+    step = max(1 << 20, -(-n // n_thr))
     chunks = [(i, min(n, i + step)) for i in range(0, n, step)]
     if len(chunks) > 1:
         from concurrent.futures import ThreadPoolExecutor
 
-        with ThreadPoolExecutor(max_workers=min(8, len(chunks))) as pool:
+        with ThreadPoolExecutor(max_workers=min(n_thr, len(chunks))) as pool:
             list(pool.map(lambda ab: np.copyto(out[ab[0] : ab[1]], src[ab[0] : ab[1]]), chunks))
     else:
         np.copyto(out, src)
     return out.reshape(t.shape)
+
+
+def _copy_threads() -> int:
+    """Host copy threads of this rank: at most 8, and no more than its share of the cores when several ranks (LOCAL_WORLD_SIZE
+    / WORLD_SIZE of torchrun) run on the box."""
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return max(1, min(8, (os.cpu_count() or 8) // max(1, ranks)))
 
 
 def _to_host_into(t, dst: np.ndarray, slab_bytes: int = 256 << 20):

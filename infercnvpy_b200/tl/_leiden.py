@@ -159,21 +159,47 @@ def leiden(
 
     from ._pca import _device
 
+    from ..pp._neighbors import _unsupported_kwargs, allgather_rows
+
     resolution = float(kwargs.pop("resolution", 1.0))
+    _unsupported_kwargs("leiden", kwargs, {"random_state": None, "n_iterations": (-1,), "directed": None, "use_weights": (True,),
+                                           "flavor": ("leidenalg",), "restrict_to": (None,), "adjacency": (None,),
+                                           "partition_type": (None,), "obsp": (None,), "copy": (False,)})
     if neighbors_key not in adata.uns:
         raise KeyError(f"No neighbors graph under {neighbors_key!r}. Did you run `pp.neighbors`?")
     ckey = adata.uns[neighbors_key].get("connectivities_key", f"{neighbors_key}_connectivities")
-    A = adata.obsp[ckey]
+    A = sp.csr_matrix(adata.obsp[ckey])
     device = _device()
-    indptr, indices, w = _csr_to_device(sp.csr_matrix(A), device)
+    shard = adata.uns[neighbors_key].get("shard")
+    if shard is not None:
+        # row shard of the global graph: gather the COO triples of all ranks, cluster the whole graph on every rank
+        # (deterministic -> identical labels) and keep this rank's rows
+        coo = A.tocoo()
+        r = torch.from_numpy(coo.row.astype(np.int64) + int(shard["row0"])).to(device)
+        c = torch.from_numpy(coo.col.astype(np.int64)).to(device)
+        v = torch.from_numpy(coo.data.astype(np.float32)).to(device)
+        r, _ = allgather_rows(r)
+        c, _ = allgather_rows(c)
+        v, _ = allgather_rows(v)
+        n_total = int(shard["n_total"])
+        order = torch.argsort(r * n_total + c)
+        counts = torch.bincount(r, minlength=n_total)
+        indptr = torch.zeros(n_total + 1, dtype=torch.int64, device=device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        indices, w = c[order].to(torch.int32), v[order]
+    else:
+        indptr, indices, w = _csr_to_device(A, device)
     labels = leiden_device(indptr, indices, w, gamma=resolution)
     # number clusters by decreasing size (leidenalg convention)
     counts = torch.bincount(labels)
     order = torch.argsort(counts, descending=True, stable=True)
     rank = torch.empty_like(order)
     rank[order] = torch.arange(order.numel(), device=device)
-    lab = rank[labels].cpu().numpy()
-    cats = [str(i) for i in range(int(lab.max()) + 1)] if lab.size else []
+    lab = rank[labels]
+    if shard is not None:
+        lab = lab[int(shard["row0"]) : int(shard["row0"]) + adata.shape[0]]
+    lab = lab.cpu().numpy()
+    cats = [str(i) for i in range(int(order.numel()))]
     result = pd.Categorical([str(i) for i in lab], categories=cats)
     if inplace:
         adata.obs[key_added] = result

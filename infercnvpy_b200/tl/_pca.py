@@ -23,7 +23,7 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _allreduce(t):
+def _allreduce_sum(t):
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -34,6 +34,9 @@ def _allreduce(t):
             dist.all_reduce(c)
             t.copy_(c)
     return t
+
+
+_allreduce = _allreduce_sum  # name used by pp/_neighbors.py
 
 
 def matrix_to_device_dense(X, device):
@@ -60,9 +63,9 @@ def matrix_to_device_dense(X, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(X), dtype=np.float32)).to(device)
 
 
-def pca_device(Xd, n_comps: int, zero_center: bool = False, n_total: int | None = None):
+def pca_device(Xd, n_comps: int, zero_center: bool = False, n_total: int | None = None, reduce: bool = True):
     """Device-level PCA: ``Xd`` float32 ``[n, K]`` (this rank's rows) -> ``(Y [n, n_comps] float32, V [K, n_comps] f64,
-    singular values)``."""
+    singular values)``.  ``reduce=False`` keeps the decomposition local even inside a process group (tests)."""
     import torch
 
     lib = _lib.load()
@@ -71,6 +74,7 @@ def pca_device(Xd, n_comps: int, zero_center: bool = False, n_total: int | None 
     stream = _lib.stream_handle(device)
     C = torch.empty((K, K), dtype=torch.float64, device=device)
     _lib.check(lib.icnv_gram_f32(_lib.ptr(Xd), n, Xd.stride(0), K, _lib.ptr(C), stream), "icnv_gram_f32")
+    _allreduce = _allreduce_sum if reduce else (lambda t: t)
     _allreduce(C)
     mu = None
     if zero_center:
@@ -112,13 +116,19 @@ def pca(
 
     Same parameters / keys / errors as the reference (``tl/__init__.py:33-75``); ``svd_solver`` is accepted for
     compatibility (the decomposition is always the exact symmetric eigenproblem of the Gram matrix);
-    ``n_comps`` (scanpy keyword, default ``min(50, min(shape) - 1)``) may be passed through ``**kwargs``.
+    ``n_comps`` (scanpy keyword, default ``min(50, min(shape) - 1)``) may be passed through ``**kwargs``; other scanpy
+    keywords raise ``TypeError`` unless they carry the value implemented here.  Under an initialised ``torch.distributed``
+    group every rank passes its row shard: the ``K x K`` Gram matrix is all-reduced and every rank projects its rows.
     """
     if f"X_{use_rep}" not in adata.obsm:
         raise KeyError(f"X_{use_rep} is not in adata.obsm. Did you run `tl.infercnv`?")
     X = adata.obsm[f"X_{use_rep}"]
     n, K = X.shape
+    from ..pp._neighbors import _unsupported_kwargs
+
     n_comps = kwargs.pop("n_comps", None)
+    _unsupported_kwargs("pca", kwargs, {"random_state": None, "dtype": ("float32",), "chunked": (False,), "mask_var": (None,),
+                                        "use_highly_variable": (None, False), "return_info": (False,), "copy": (False,)})
     if n_comps is None:
         n_comps = min(50, min(n, K) - 1)
     if not 1 <= n_comps <= min(64, K):

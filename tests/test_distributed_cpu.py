@@ -109,3 +109,31 @@ def test_sharded_label_order_and_category_validation_world2(tmp_path):
     port = _free_port()
     mp.spawn(_label_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+def _gather_worker(rank, world, port, out_dir):
+    """allgather_rows (pp/_neighbors.py): ragged row shards of coordinates / kNN lists are concatenated in rank order."""
+    from infercnvpy_b200.pp._neighbors import allgather_rows
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
+        cut = [0, 5, 7]  # 5 rows on rank 0, 2 on rank 1
+        mine = full[cut[rank] : cut[rank + 1]]
+        got, row0 = allgather_rows(mine)
+        assert row0 == cut[rank] and torch.equal(got, full)
+        ids = torch.arange(cut[rank], cut[rank + 1], dtype=torch.int64)
+        got_ids, _ = allgather_rows(ids)
+        assert torch.equal(got_ids, torch.arange(7))
+        empty, r0 = allgather_rows(full[:0] if rank == 1 else full)  # a rank without rows
+        assert torch.equal(empty, full) and r0 == (0 if rank == 0 else 7)
+        open(os.path.join(out_dir, f"g_{rank}"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_rows_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "g_0").exists() and (tmp_path / "g_1").exists()

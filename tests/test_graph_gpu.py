@@ -70,7 +70,7 @@ def test_knn_is_exact_on_random_points(n, d, k):
 
 def test_knn_tensor_core_path_at_scale_and_sharded():
     """20 011 clustered points x 50 dims (not a multiple of the 128-point tile): the tcgen05 distance GEMM + exact re-rank
-    against a float64 brute force on the device; then the same lists from two query shards (q0 a multiple of 128), which
+    against a float64 brute force on the device; then the same lists from two query shards, which
     is how ranks split the queries after the all-gather of the coordinates."""
     import torch
     from infercnvpy_b200.pp._neighbors import knn_device
@@ -92,8 +92,8 @@ def test_knn_tensor_core_path_at_scale_and_sharded():
     np.testing.assert_allclose((dist.double() ** 2).cpu().numpy(), want_d.cpu().numpy(), rtol=2e-5, atol=1e-5)
     same = (idx.long() == want_i).float().mean().item()
     assert same > 0.9999, same  # identities can only differ between exact ties
-    i0, d0 = knn_device(Pd, k, q0=0, nq=128 * 80)
-    i1, d1 = knn_device(Pd, k, q0=128 * 80, nq=n - 128 * 80)
+    i0, d0 = knn_device(Pd, k, q0=0, nq=10000)  # shard boundaries are multiples of chunksize, not of the 128-point tile
+    i1, d1 = knn_device(Pd, k, q0=10000, nq=n - 10000)
     assert torch.equal(torch.cat([i0, i1]), idx) and torch.equal(torch.cat([d0, d1]), dist)
 
 

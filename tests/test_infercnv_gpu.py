@@ -652,3 +652,27 @@ def test_ith_scores_known_answers_and_golden():
         assert np.isnan(res[k]) == np.isnan(want[k])
         if not np.isnan(want[k]):
             assert float(res[k]) == pytest.approx(float(want[k]), rel=1e-9)
+
+
+def test_group_means_match_numpy(golden_loader):
+    """pl.chromosome_heatmap_summary's per-group column means (/root/reference/src/infercnvpy/pl/_chromosome_heatmap.py:
+    149-158) against the reference expression evaluated with numpy/scipy on the same CSR, sparse and dense containers."""
+    case = next(c for c in CASES if c["name"] == "small_default")
+    X, var, obs, kw = build_case(case)
+    adata = _adata(X, var, obs)
+    cnv.tl.infercnv(adata, **kw)
+    rng = np.random.default_rng(4)
+    adata.obs = pd.DataFrame({"grp": rng.choice(["b", "a", "z", "m"], size=X.shape[0])}, index=adata.obs.index)
+    res = cnv.pl.chromosome_heatmap_summary(adata, groupby="grp")
+    assert res["groups"] == list(adata.obs["grp"].unique())
+    Xc = adata.obsm["X_cnv"]
+    for i, g in enumerate(res["groups"]):
+        want = np.asarray(np.mean(Xc[adata.obs["grp"].values == g, :], axis=0)).ravel()
+        np.testing.assert_allclose(res["mean"][i], want, rtol=1e-12, atol=1e-15)
+    assert res["var_group_positions"][0][0] == 0 and res["var_group_positions"][-1][1] == Xc.shape[1]
+    assert res["var_group_labels"] == list(adata.uns["cnv"]["chr_pos"].keys())
+    adata.obsm["X_dense"] = Xc.toarray()
+    g2, m2 = cnv.pl.group_means(adata, "grp", use_rep="dense")
+    np.testing.assert_allclose(m2, res["mean"], rtol=1e-12, atol=1e-15)
+    with pytest.raises(ValueError, match="cnv_leiden"):
+        cnv.pl.chromosome_heatmap_summary(adata)
