@@ -259,15 +259,29 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __
             for (int c0 = 0; c0 < KNN_TILE; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * KNN_TILE + c0), r);
+                // 32 independent keys, one min tree, ONE branch per chunk: the single epilogue warp of a scheduler has
+                // nobody to hide latencies behind, so a compare-and-branch per key (dependent FFMA -> FSETP -> BRA) cost
+                // ~35 cycles per key (ncu r2); the per-key tests only run for the chunks that hold a candidate
+                float key[32];
 #pragma unroll
                 for (int j4 = 0; j4 < 32; j4 += 4) {
                     const float4 n4 = *reinterpret_cast<const float4*>(cn + c0 + j4);
-                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+                    key[j4 + 0] = fmaf(-2.f, __uint_as_float(r[j4 + 0]), n4.x);
+                    key[j4 + 1] = fmaf(-2.f, __uint_as_float(r[j4 + 1]), n4.y);
+                    key[j4 + 2] = fmaf(-2.f, __uint_as_float(r[j4 + 2]), n4.z);
+                    key[j4 + 3] = fmaf(-2.f, __uint_as_float(r[j4 + 3]), n4.w);
+                }
+                float mn[16];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float key = fmaf(-2.f, __uint_as_float(r[j4 + u]), nn[u]);
-                        if (key < thr) thr = knn_insert(lkey, lidx, lmeta, row, key, (int32_t)(t * KNN_TILE + c0 + j4 + u));
-                    }
+                for (int j = 0; j < 16; ++j) mn[j] = fminf(key[j], key[j + 16]);
+#pragma unroll
+                for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+                    for (int j = 0; j < w; ++j) mn[j] = fminf(mn[j], mn[j + w]);
+                if (mn[0] < thr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (key[j] < thr) thr = knn_insert(lkey, lidx, lmeta, row, key[j], (int32_t)(t * KNN_TILE + c0 + j));
                 }
             }
             tc_fence_before();
