@@ -234,7 +234,7 @@ def main():
             "chunksize": CHUNK, "dynamic_threshold": DYN, "lfc_clip": LFC,
             "reference": "mean of all cells (computed every step, all-reduced when N>1)",
             "sharding": f"rows of ONE {cells_total}-cell matrix over {world} rank(s), shard boundaries multiples of chunksize",
-            "step_contents": "colsum + all-reduce + mean + set_reference + smooth + row-median centring + chunk threshold + filter + dense->CSR",
+            "step_contents": "colsum + all-reduce + mean + set_reference + smooth + row-median centring + chunk threshold + filter count + indptr scan + filtering dense->CSR compaction",
             "l2": f"input {cells_total // world * G_GENES * 4 / 1e9:.0f} GB per GPU per step >> 126 MB L2 (no flush needed)",
         }
 
@@ -342,16 +342,17 @@ def main():
             plan.smooth(Xin, LFC, tmp=tmp)                      # 1  <- dominant kernel (steps 1-3)
             ev_s1[i].record()
             plan.center(tmp, out=out, row_stats=stats)          # 1  (step 4: exact row median)
-            thr, row_abs, row_nnz = plan.threshold(out, stats, CHUNK, DYN)  # 2  (step 5)
+            # step 5 + :455: chunk thresholds (1), counting pass (1), indptr scan (1), filtering compaction (1)
             if "indices" not in csr_buf:                        # first warm-up step sizes the CSR buffers (+25 %)
-                indptr, indices, data = plan.to_csr(out, row_nnz)
+                thr, row_abs, row_nnz, (indptr, indices, data) = plan.filter_to_csr(out, stats, CHUNK, DYN)
                 cap = int(indices.numel() * 1.25) + 1024
                 csr_buf["indices"] = torch.empty((cap,), dtype=torch.int32, device=dev)
                 csr_buf["data"] = torch.empty((cap,), dtype=torch.float32, device=dev)
                 csr_buf["indptr"] = torch.empty((n_local + 1,), dtype=torch.int64, device=dev)
                 del indices, data, indptr
-            else:                                               # 2  (:455: scan of the row counts + compaction)
-                plan.to_csr(out, row_nnz, indptr=csr_buf["indptr"], indices=csr_buf["indices"], data=csr_buf["data"])
+            else:
+                thr, row_abs, row_nnz, _ = plan.filter_to_csr(out, stats, CHUNK, DYN, indptr=csr_buf["indptr"],
+                                                              indices=csr_buf["indices"], data=csr_buf["data"])
             return row_abs
 
         for i in range(args.warmup):
@@ -528,6 +529,8 @@ def main():
         e2e = {
             "value": int(rows_all[0]) / sec, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "seconds_per_step": sec, "cells_per_step_all_ranks": int(rows_all[0]), "cells_per_step_per_rank": n_e2e, "steps": e2e_steps,
+            "h2d_only_seconds": link_sec, "h2d_only_GBps_per_rank": (h2d / link_sec / 1e9 if link_sec else None),
+            "h2d_only_note": "plain pinned->device copy of the same input, all ranks concurrently (max over ranks): the share of seconds_per_step the host link alone takes",
             "api": "infercnvpy_b200.tl.infercnv(adata) with adata.X in pinned host memory; result scipy CSR float64 on host; "
                    f"every rank runs its {'whole shard' if n_e2e == n_local else f'first {n_e2e} rows of its shard (host memory bound)'}",
         }

@@ -128,6 +128,18 @@ int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t 
                          int64_t chunk_rows, const double* thr, double* row_abs_sum, int32_t* row_nnz,
                          void* stream);
 
+/* The same filter WITHOUT rewriting the matrix (the CSR path of tl.infercnv never needs the filtered dense block):
+ * icnv_filter_count only counts -- per row the number and the sum|v| of the values that survive |v| < thr (strict,
+ * :451; zeros never count) -- and icnv_filter_to_csr applies the same predicate again while compacting every row into
+ * (indices, data) (:455; indptr = icnv_nnz_to_indptr of the counts).  data is float32 or float64 (data_is_f64; a float64
+ * matrix needs float64 data).  thr == NULL: every non-zero survives.  Against icnv_apply_threshold + icnv_dense_to_csr
+ * this saves one write and one read of the [n_rows, K] matrix. */
+int icnv_filter_count(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                      const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream);
+int icnv_filter_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                       const double* thr, const int64_t* indptr, int32_t* indices, void* data, int32_t data_is_f64,
+                       void* stream);
+
 /* Per-gene layer of calculate_gene_values=True, tl/_infercnv.py:141-151, :214-223, :238-242, :247-291, :443-444, :452-453.
  * From the smoothed rows in `tmp` (icnv_smooth_*): value(gene) = np.mean (numpy's pairwise order) of the kept windows that
  * contain the gene (:278-287; the flat mean on chromosomes not longer than the window, :240), minus the median of the

@@ -224,6 +224,58 @@ class DevicePlan:
             )
         return thr, row_abs, row_nnz
 
+    def chunk_thresholds(self, row_stats, n: int, K: int, chunk_rows: int, dynamic_threshold):
+        """Per-chunk noise thresholds ``dynamic_threshold * std(chunk)`` (``:450``) from the row moments; ``None`` when the
+        filter is off."""
+        torch = _torch()
+        if dynamic_threshold is None or n == 0:
+            return None
+        thr = torch.empty((math.ceil(n / chunk_rows),), dtype=torch.float64, device=self.device)
+        _lib.check(
+            self.lib.icnv_chunk_threshold(_lib.ptr(row_stats), n, K, chunk_rows, float(dynamic_threshold), _lib.ptr(thr), self._stream()),
+            "icnv_chunk_threshold",
+        )
+        self.launches += 1
+        return thr
+
+    def filter_to_csr(self, out, row_stats, chunk_rows: int, dynamic_threshold, indptr=None, indices=None, data=None, data_dtype=None):
+        """Steps 5 + CSR (``:449-455``) without rewriting ``out``: thresholds, a counting pass, the indptr scan and one
+        compaction pass that applies the filter on the fly.  Returns ``(thr, row_abs_sum, row_nnz, (indptr, indices, data))``.
+        With caller-provided ``indices`` / ``data`` nothing is read back (asynchronous); ``data_dtype`` float64 widens on
+        the device (the reference's container dtype)."""
+        torch = _torch()
+        n, K = out.shape
+        is64 = int(out.dtype == torch.float64)
+        thr = self.chunk_thresholds(row_stats, n, K, chunk_rows, dynamic_threshold)
+        row_abs = torch.empty((n,), dtype=torch.float64, device=self.device)
+        row_nnz = torch.empty((n,), dtype=torch.int32, device=self.device)
+        if indptr is None:
+            indptr = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
+        if n:
+            _lib.check(
+                self.lib.icnv_filter_count(_lib.ptr(out), is64, n, K, out.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(row_abs),
+                                           _lib.ptr(row_nnz), self._stream()),
+                "icnv_filter_count",
+            )
+            self.launches += 1
+        _lib.check(self.lib.icnv_nnz_to_indptr(_lib.ptr(row_nnz), n, _lib.ptr(indptr), self._stream()), "icnv_nnz_to_indptr")
+        self.launches += 1
+        if indices is None:
+            nnz = int(indptr[-1].item())
+            indices = torch.empty((nnz,), dtype=torch.int32, device=self.device)
+            data = torch.empty((nnz,), dtype=data_dtype or out.dtype, device=self.device)
+        else:
+            assert data is not None and indices.dtype == torch.int32
+            nnz = indices.numel()
+        if n and nnz:
+            _lib.check(
+                self.lib.icnv_filter_to_csr(_lib.ptr(out), is64, n, K, out.stride(0), chunk_rows, _lib.ptr(thr), _lib.ptr(indptr),
+                                            _lib.ptr(indices), _lib.ptr(data), int(data.dtype == torch.float64), self._stream()),
+                "icnv_filter_to_csr",
+            )
+            self.launches += 1
+        return thr, row_abs, row_nnz, (indptr, indices, data)
+
     def gene_values(self, tmp, chunk_rows: int, thr=None, out=None):
         """Per-gene layer of ``calculate_gene_values=True`` for the rows of ``tmp`` (output of :meth:`smooth`):
         ``[n, n_genes]`` float64 in the matrix's column order, NaN where no kept window covers the gene.

@@ -37,6 +37,8 @@ SIGNATURES = {
     "icnv_center_rows": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, c_vp, C.c_int32, C.c_int64, c_vp, c_vp]),
     "icnv_chunk_threshold": (C.c_int, [c_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, c_vp, c_vp]),
     "icnv_apply_threshold": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
+    "icnv_filter_count": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp]),
+    "icnv_filter_to_csr": (C.c_int, [c_vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, c_vp, c_vp, C.c_int32, c_vp]),
     "icnv_gene_values": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int64, C.c_int64, c_vp, c_vp, C.c_int64, c_vp]),
     "icnv_plan_gene_coverage": (C.c_int, [c_vp, c_i32p]),
     "icnv_plan_gather_cost": (C.c_int, [c_vp, C.POINTER(C.c_double)]),

@@ -28,6 +28,8 @@ int aux_build_bounds(const void*, bool, int, int, const int32_t*, int64_t, void*
 int aux_chunk_threshold(const double*, int64_t, int64_t, int64_t, double, double*, cudaStream_t);
 int aux_center_rows(const double*, int64_t, int64_t, const Task*, int, int, void*, bool, int64_t, double*, cudaStream_t);
 int aux_apply_threshold(void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
+int filter_count(const void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
+int filter_to_csr(const void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, const int64_t*, int32_t*, void*, bool, cudaStream_t);
 int smooth_raw_base(uint32_t* base);
 int aux_dense_to_csr(const void*, bool, int64_t, int64_t, int64_t, const int64_t*, int32_t*, void*, cudaStream_t);
 int aux_rowabs_csr(const int64_t*, const void*, bool, int64_t, double*, cudaStream_t);
@@ -484,7 +486,8 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
         std::vector<uint8_t> order;
         // ICNV_GATHER_PERM=0 (developer A/B): keep the natural walk; the entries still carry j
         const char* perm_env = std::getenv("ICNV_GATHER_PERM");
-        const bool optimise_walk = p->permuted && !(perm_env && perm_env[0] == '0');
+        const bool natural_walk = ICNV_NATURAL_WALK == 2 || (ICNV_NATURAL_WALK == 1 && p->qstar >= 0);  // kernels take j from the loop
+        const bool optimise_walk = p->permuted && !natural_walk && !(perm_env && perm_env[0] == '0');
         p->gather_wavefronts = schedule_gathers(gcol, p->NG, gs, n_genes, nsets, optimise_walk, slot_group, order);
         if (p->gather_wavefronts < 0) {
             set_error("internal: group slots exhausted");
@@ -530,7 +533,7 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
                             off[e] = raw_base + (uint32_t)col * 4u;
                             cols[e] = col;
                         }
-                        if (p->permuted) off[e] |= ((uint32_t)j << 24) | ((uint32_t)mj[j] << 28);  // pads too (x = 0 either way)
+                        if (p->permuted && !natural_walk) off[e] |= ((uint32_t)j << 24) | ((uint32_t)mj[j] << 28);  // pads too (x = 0 either way)
                     }
                 }
         auto& T = p->tab[ts];
@@ -983,6 +986,24 @@ int icnv_apply_threshold(void* out, int32_t out_is_f64, int64_t n_rows, int64_t 
         return ICNV_EINVAL;
     }
     return aux_apply_threshold(out, out_is_f64 != 0, n_rows, K, ldo, chunk_rows, thr, row_abs_sum, row_nnz, (cudaStream_t)stream);
+}
+
+int icnv_filter_count(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                      const double* thr, double* row_abs_sum, int32_t* row_nnz, void* stream) {
+    if ((n_rows > 0 && !out) || chunk_rows < 1 || ldo < K) {
+        set_error("icnv_filter_count: bad argument");
+        return ICNV_EINVAL;
+    }
+    return filter_count(out, out_is_f64 != 0, n_rows, K, ldo, chunk_rows, thr, row_abs_sum, row_nnz, (cudaStream_t)stream);
+}
+
+int icnv_filter_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, int64_t chunk_rows,
+                       const double* thr, const int64_t* indptr, int32_t* indices, void* data, int32_t data_is_f64, void* stream) {
+    if ((n_rows > 0 && (!out || !indptr)) || chunk_rows < 1 || ldo < K || (out_is_f64 && !data_is_f64)) {
+        set_error("icnv_filter_to_csr: bad argument");
+        return ICNV_EINVAL;
+    }
+    return filter_to_csr(out, out_is_f64 != 0, n_rows, K, ldo, chunk_rows, thr, indptr, indices, data, data_is_f64 != 0, (cudaStream_t)stream);
 }
 
 int icnv_dense_to_csr(const void* out, int32_t out_is_f64, int64_t n_rows, int64_t K, int64_t ldo, const int64_t* indptr,

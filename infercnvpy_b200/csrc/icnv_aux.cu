@@ -95,45 +95,8 @@ __global__ void mean_from_sums_kernel(const double* __restrict__ sums, const int
     ref[i] = (T)(sums[i] / (double)counts[c]);
 }
 
-// row_nnz -> CSR indptr: single CTA, chunked inclusive scan (n_rows is at most a few million)
-__global__ void __launch_bounds__(1024) nnz_to_indptr_kernel(const int32_t* __restrict__ row_nnz, int64_t n_rows,
-                                                             int64_t* __restrict__ indptr) {
-    __shared__ long long warp_tot[32];
-    __shared__ long long carry_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        carry_s = 0;
-        indptr[0] = 0;
-    }
-    __syncthreads();
-    for (int64_t base = 0; base < n_rows; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        long long v = i < n_rows ? (long long)row_nnz[i] : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += t;
-        }
-        if (lane == 31) warp_tot[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            long long w = warp_tot[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            warp_tot[lane] = w;
-        }
-        __syncthreads();
-        const long long carry = carry_s;
-        const long long incl = v + (warp > 0 ? warp_tot[warp - 1] : 0) + carry;
-        if (i < n_rows) indptr[i + 1] = incl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = incl;
-        __syncthreads();
-    }
-}
+// row_nnz -> CSR indptr: indptr_scan_kernel (icnv_filter.cu)
+int indptr_scan(const int32_t* row_nnz, int64_t n_rows, int64_t* indptr, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------
 // Per-gene centring bounds in the layouts the smoothing kernel reads.
@@ -834,9 +797,7 @@ int aux_mean_from_sums(const double* sums, const int64_t* counts, int n_cat, int
     return 0;
 }
 int aux_nnz_to_indptr(const int32_t* row_nnz, int64_t n_rows, int64_t* indptr, cudaStream_t st) {
-    nnz_to_indptr_kernel<<<1, 1024, 0, st>>>(row_nnz, n_rows, indptr);
-    ICNV_CUDA(cudaGetLastError());
-    return 0;
+    return indptr_scan(row_nnz, n_rows, indptr, st);
 }
 
 int aux_build_bounds(const void* ref, bool ref_f64, int n_cat, int G, const int32_t* cols, int64_t n, void* lo, void* hi,

@@ -21,6 +21,11 @@ __host__ __device__ constexpr int smooth_threads(int rows, bool dbuf = false) { 
 // Row pairs of a window whose pyramid peak falls inside a group (third partial sum per group) keep half units: 12 fp64
 // accumulators per lane instead of 16 + 8.
 #define ICNV_UNIT_WIDTH(rows, peak_group) (((rows) == 2 && !(peak_group)) ? 4 : 2)
+// gather walk of the templated kernels: 0 = conflict-aware permuted walk everywhere (entries carry j / m_j, decoded per
+// entry), 1 = natural walk for windows with a peak group (window 250), 2 = natural walk everywhere
+#ifndef ICNV_NATURAL_WALK
+#define ICNV_NATURAL_WALK 0
+#endif
 #ifndef ICNV_LOUT
 #define ICNV_LOUT 9
 #endif

@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(smooth_threads(ROWS, DBUF), (TIER == 0 && TPT 
     constexpr int UW = ICNV_UNIT_WIDTH(ROWS, M3_C);
     // permuted walk (icnv_schedule.cu): step t of a lane reads element j = (entry >> 24) & 15 of its group, not element t;
     // with a peak group bits 28..31 carry m_j = cw_j - cw_0, the non-linear part of the weights inside that group
-    constexpr bool PERM = (TIER == 0);
+    // ICNV_NATURAL_WALK (icnv_common.cuh): 1 = kernels with a peak group walk their groups in natural order (j and m_j are
+    // compile-time immediates: no per-entry decode, at the price of ~2 instead of ~1.2 wavefronts per gather), 2 = all
+    constexpr bool PERM = (TIER == 0) && !(ICNV_NATURAL_WALK == 2 || (ICNV_NATURAL_WALK == 1 && M3_C));
     // row pairs with a peak group: the third partial sum lives in a global (L2) scratch, see SmoothParams::c_scratch
     constexpr bool CGLOBAL = M3_C && ROWS == 2;
 #define ICNV_ABS (p.NGpad + PAD_GROUPS) /* partial-sum slots per staged row */
@@ -325,13 +327,14 @@ __global__ void __launch_bounds__(smooth_threads(ROWS, DBUF), (TIER == 0 && TPT 
                                 else if (j > 0)
                                     b[rr][u] = fma((double)j, dd, b[rr][u]);
                                 if constexpr (PERM && M3_C) c[rr][u] = fma(md[u], dd, c[rr][u]);
-                                else if (qstar >= 0) c[rr][u] = fma(cwj, dd, c[rr][u]);
+                                else if (qstar >= 0 && (TIER != 0 || cwj != 0.0)) c[rr][u] = fma(cwj, dd, c[rr][u]);
                             }
                         }
                 };
                 if constexpr (TIER == 0) {
 #pragma unroll
-                    for (int j = 0; j < GS; ++j) body(j, 0.0);
+                    for (int j = 0; j < GS; ++j)  // cwj: the peak group's non-linear weight m_j (natural walk only)
+                        body(j, M3_C ? (double)(pyr(NWIN, GS * (M3_C ? QSTAR_C : 0) + j) - pyr(NWIN, GS * (M3_C ? QSTAR_C : 0))) : 0.0);
                 } else {
                     for (int j = 0; j < gs; ++j) body(j, w_c[j]);
                 }

@@ -60,6 +60,7 @@ def _rows_to_device(expr, r0, r1, device):
     if isinstance(expr, torch.Tensor):
         return expr[r0:r1].to(device=device, dtype=torch.float32).contiguous()
     blk = np.ascontiguousarray(np.asarray(expr[r0:r1]), dtype=np.float32)
+    LAST_TRANSFER["h2d_bytes"] += blk.nbytes
     return torch.from_numpy(blk).to(device)
 
 
@@ -71,6 +72,7 @@ def _upload_1d(arr: np.ndarray, device):
     arr = np.ascontiguousarray(arr)
     src = torch.from_numpy(arr)
     n = src.numel()
+    LAST_TRANSFER["h2d_bytes"] += arr.nbytes
     if n * src.element_size() < (64 << 20):
         return src.to(device)
     dst = torch.empty((n,), dtype=src.dtype, device=device)
@@ -116,6 +118,7 @@ def _upload_pipelined(expr: np.ndarray, device, on_slab):
     import torch
 
     n, G = expr.shape
+    LAST_TRANSFER["h2d_bytes"] += expr.nbytes
     Xd = torch.empty((n, G), dtype=torch.float32, device=device)
     src = torch.from_numpy(expr)
     pinned = src.is_pinned()
@@ -155,37 +158,73 @@ def _upload_pipelined(expr: np.ndarray, device, on_slab):
 
 
 _PINNED: dict = {}
+_POOL: dict = {}
+LAST_TRANSFER = {"h2d_bytes": 0, "d2h_bytes": 0}  # bytes the last infercnv() call moved over PCIe (bench.py reports them)
 
 
-def _to_host(t):
-    """Device tensor -> numpy through a cached pinned buffer (async DMA instead of a pageable copy)."""
+def _pool():
+    """Host copy threads of this process (created once)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    n = _copy_threads()
+    if _POOL.get("n") != n:
+        _POOL["n"] = n
+        _POOL["pool"] = ThreadPoolExecutor(max_workers=n)
+    return _POOL["pool"], n
+
+
+def _to_host(t, out_dtype=None, slab_bytes: int = 32 << 20):
+    """Device tensor -> fresh numpy array (optionally widened to ``out_dtype`` on the host, so float32 values cross PCIe
+    as 4 bytes and land as the reference's float64).  The tensor is copied in slabs through two cached pinned buffers:
+    the DMA of slab i+1 overlaps the host threads that move slab i into the (first-touched) result array."""
     import torch
 
     n = t.numel()
+    src_np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
+    out_dtype = np.dtype(out_dtype or src_np_dtype)
     if n < (1 << 16):
-        return t.cpu().numpy()
-    key = t.dtype
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty((int(n * 1.25),), dtype=t.dtype, pin_memory=True)
-        _PINNED[key] = buf
-    view = buf[:n]
-    view.copy_(t.reshape(-1), non_blocking=True)
-    torch.cuda.current_stream(t.device).synchronize()
-    src = view.numpy()
-    out = np.empty(n, dtype=src.dtype)
-    # first touch of a fresh host array is page-fault bound (~5 GB/s per thread): spread it over a few threads — the
-    # host cores are shared by all ranks of the box (one process per GPU), so each rank takes its share of them
-    n_thr = _copy_threads()
-    step = max(1 << 20, -(-n // n_thr))
-    chunks = [(i, min(n, i + step)) for i in range(0, n, step)]
-    if len(chunks) > 1:
-        from concurrent.futures import ThreadPoolExecutor
+        return t.cpu().numpy().astype(out_dtype, copy=False)
+    LAST_TRANSFER["d2h_bytes"] += n * t.element_size()
+    flat = t.reshape(-1)
+    per = max(1, slab_bytes // t.element_size())
+    key = (t.dtype, per)
+    bufs = _PINNED.get(key)
+    if bufs is None:
+        bufs = [torch.empty((per,), dtype=t.dtype, pin_memory=True) for _ in range(2)]
+        _PINNED[key] = bufs
+    out = np.empty(n, dtype=out_dtype)
+    pool, n_thr = _pool()
+    spans = [(a, min(n, a + per)) for a in range(0, n, per)]
+    evs = [None, None]
+    main = torch.cuda.current_stream(t.device)
+    side = _PINNED.setdefault(("stream", str(t.device)), torch.cuda.Stream(t.device))
+    side.wait_stream(main)
 
-        with ThreadPoolExecutor(max_workers=min(n_thr, len(chunks))) as pool:
-            list(pool.map(lambda ab: np.copyto(out[ab[0] : ab[1]], src[ab[0] : ab[1]]), chunks))
-    else:
-        np.copyto(out, src)
+    def issue(i):
+        a, b = spans[i]
+        with torch.cuda.stream(side):
+            bufs[i % 2][: b - a].copy_(flat[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        evs[i % 2] = ev
+
+    def move(i):
+        a, b = spans[i]
+        src = bufs[i % 2][: b - a].numpy()
+        step = max(1 << 18, -(-(b - a) // n_thr))
+        parts = [(x, min(b - a, x + step)) for x in range(0, b - a, step)]
+        if len(parts) > 1:
+            list(pool.map(lambda xy: np.copyto(out[a + xy[0] : a + xy[1]], src[xy[0] : xy[1]], casting="same_kind"), parts))
+        else:
+            np.copyto(out[a:b], src, casting="same_kind")
+
+    issue(0)
+    for i in range(len(spans)):
+        evs[i % 2].synchronize()
+        if i + 1 < len(spans):
+            issue(i + 1)  # the other buffer: its previous content was moved out in the last iteration
+        move(i)
+    main.wait_stream(side)  # the source tensor may be freed / reused by the caller from here on
     return out.reshape(t.shape)
 
 
@@ -227,15 +266,16 @@ def _to_host_into(t, dst: np.ndarray, slab_bytes: int = 256 << 20):
 
 
 def _host_csr(indptr, indices, data, shape):
-    """Device CSR pieces -> scipy CSR float64 (the reference's container, _infercnv.py:455); the float64
-    widening happens on the device so the host never touches the values."""
+    """Device CSR pieces -> scipy CSR float64 (the reference's container, _infercnv.py:455)."""
     import torch
 
-    small = int(indptr[-1].item()) < 2**31 - 1 if indptr.numel() else True
+    small = indices.numel() < 2**31 - 1
     ip = _to_host(indptr.to(torch.int32) if small else indptr)
     ix = _to_host(indices if small else indices.to(torch.int64))
-    dv = _to_host(data.to(torch.float64))
-    return scipy.sparse.csr_matrix((dv, ix, ip), shape=shape)
+    dv = _to_host(data, np.float64)  # float32 on the wire, widened by the host copy threads
+    res = scipy.sparse.csr_matrix((dv, ix, ip), shape=shape, copy=False)
+    res.has_sorted_indices = True  # compacted in column order
+    return res
 
 
 _PLAN_CACHE: dict = {}
@@ -334,6 +374,7 @@ def infercnv(
     if device is None:
         raise _lib.IcnvError("infercnvpy_b200.tl.infercnv needs a CUDA device; there is no CPU fallback")
     layout, plan = _cached_plan(adata.var, window_size, step, exclude_chromosomes, device)
+    LAST_TRANSFER["h2d_bytes"] = LAST_TRANSFER["d2h_bytes"] = 0
     if layout.n_null:
         log.warning(f"Skipped {layout.n_null} genes because they don't have a genomic position annotated. ")
     chunksize = int(chunksize)
@@ -424,14 +465,14 @@ def infercnv(
             Xb = _densify(Xb, n_genes, device)
         tmp = plan.smooth(Xb, lfc_clip)
         out, stats = plan.center(tmp)
-        thr, _, row_nnz = plan.threshold(out, stats, chunksize, dynamic_threshold)
+        # noise filter + CSR in two read-only passes over `out` (count, compact); the dense block is never rewritten
+        thr, _, _, (indptr, indices, data) = plan.filter_to_csr(out, stats, chunksize, dynamic_threshold)
         if calculate_gene_values:
             # own row median (:444), the window matrix's chunk thresholds (:453); copied out in row slabs
             gv = plan.gene_values(tmp, chunksize, thr)
             _to_host_into(gv, per_gene[r0:r1])
             del gv
         del tmp
-        indptr, indices, data = plan.to_csr(out, row_nnz)
         parts.append(_host_csr(indptr, indices, data, (r1 - r0, K)))
         del out, stats, Xb
     if parts:

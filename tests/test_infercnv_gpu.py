@@ -516,6 +516,18 @@ def test_properties_at_scale():
         indptr, indices, data = plan.to_csr(out, row_nnz)
         back = torch.sparse_csr_tensor(indptr, indices.long(), data, size=out.shape).to_dense()
         assert torch.equal(back, out)
+        # (6b) the fused path (count + scan + filtering compaction on the UNFILTERED block) gives the same CSR, bit for bit
+        pre_copy = pre.clone()
+        thr2, ra2, nz2, (ip2, ix2, dv2) = plan.filter_to_csr(pre, stats, chunk, 1.5)
+        assert torch.equal(pre, pre_copy), "filter_to_csr must not rewrite the dense block"
+        assert torch.equal(thr2, thr) and torch.equal(nz2, row_nnz) and torch.equal(ip2, indptr)
+        assert torch.equal(ix2, indices) and torch.equal(dv2, data)
+        np.testing.assert_allclose(ra2.cpu().numpy(), row_abs.cpu().numpy(), rtol=1e-14)
+        _, _, _, (_, ix3, dv3) = plan.filter_to_csr(pre, stats, chunk, 1.5, data_dtype=torch.float64)
+        assert dv3.dtype == torch.float64 and torch.equal(dv3, data.double()) and torch.equal(ix3, indices)
+        # no filter: every non-zero survives
+        _, _, nz4, (ip4, ix4, dv4) = plan.filter_to_csr(pre, stats, chunk, None)
+        assert torch.equal(torch.sparse_csr_tensor(ip4, ix4.long(), dv4, size=pre.shape).to_dense(), pre)
     # (7) permuting the gene columns together with var leaves the result unchanged
     perm = np.random.default_rng(0).permutation(G)
     var_p = var.iloc[perm]
@@ -524,6 +536,23 @@ def test_properties_at_scale():
         plan_p.set_reference(ref[:, torch.from_numpy(perm).to(dev)].contiguous())
         o4 = plan_p.center(plan_p.smooth(Xd[:2000][:, torch.from_numpy(perm).to(dev)].contiguous(), 3.0))[0]
     assert torch.equal(o4, pre[:2000])
+
+
+@pytest.mark.parametrize("n", [0, 1, 1023, 8192, 8193, 70001])
+def test_indptr_scan_matches_cumsum(n):
+    torch = _torch()
+    from infercnvpy_b200 import _lib
+
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    g = torch.Generator(device=dev)
+    g.manual_seed(n)
+    nnz = torch.randint(0, 1793, (n,), generator=g, device=dev, dtype=torch.int32)
+    indptr = torch.full((n + 1,), -7, dtype=torch.int64, device=dev)
+    _lib.check(lib.icnv_nnz_to_indptr(_lib.ptr(nnz), n, _lib.ptr(indptr), _lib.stream_handle(dev)), "icnv_nnz_to_indptr")
+    want = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    want[1:] = torch.cumsum(nnz.long(), 0)
+    assert torch.equal(indptr, want)
 
 
 def test_properties_at_full_bench_size():

@@ -22,6 +22,8 @@ with DevicePlan(build_layout(var, window, 10), dev) as plan:
     out, stats = plan.center(tmp)
     thr, row_abs, row_nnz = plan.threshold(out, stats, 5000, 1.5)
     indptr, indices, data = plan.to_csr(out, row_nnz)
+    pre, stats = plan.center(tmp)
+    plan.filter_to_csr(pre, stats, 5000, 1.5)  # the fused path tl.infercnv takes (count + scan + filtering compaction)
     gv = plan.gene_values(tmp[:10000], 5000, thr)
     torch.cuda.synchronize()
     print("ok", plan.launch_info(), int(indptr[-1]), float(torch.nan_to_num(gv).abs().sum()))
