@@ -521,8 +521,25 @@ def main():
         if world > 1:
             dist.all_reduce(w, op=dist.ReduceOp.MAX)
         sec = float(w[0]) / e2e_steps
-        h2d = n_e2e * G_GENES * 4 if container == "dense" else int(Xhost.data.nbytes + Xhost.indices.nbytes + Xhost.indptr.nbytes * 2)
-        d2h = int(res.nnz * 12 + (res.shape[0] + 1) * 8)
+        from infercnvpy_b200.tl._infercnv import LAST_TRANSFER
+
+        h2d, d2h = int(LAST_TRANSFER["h2d_bytes"]), int(LAST_TRANSFER["d2h_bytes"])  # counted where the copies are issued
+        # the link's own ceiling: the same input bytes as ONE plain pinned->device copy, all ranks at the same time
+        link_sec = None
+        if container == "dense":
+            src = torch.from_numpy(Xhost)
+            dst = torch.empty(src.shape, dtype=src.dtype, device=dev)
+            dst.copy_(src, non_blocking=True)
+            barrier()
+            l0 = time.perf_counter()
+            for _ in range(2):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            lt = torch.tensor([(time.perf_counter() - l0) / 2], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            link_sec = float(lt[0])
+            del dst
         rows_all = torch.tensor([n_e2e], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(rows_all)

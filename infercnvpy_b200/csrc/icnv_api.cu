@@ -115,6 +115,12 @@ struct icnv_plan {
     DevBuf<int32_t> sp_slot_col, sp_col_slot;  // [DP] column of a slot (-1 pad); [G] slot of a column (-1: takes no part)
     DevBuf<int4> sp_col_tab;                   // [G] {slot, lo, hi, 0}, filled by icnv_plan_set_reference
     DevBuf<float> sp_zrow;                     // [DP] what a zero entry becomes, filled per smoothing call (depends on lfc_clip)
+    // delta kernel (icnv_sparse_delta.cu): one category, work proportional to the stored entries
+    bool delta_ok = false;
+    DevBuf<uint16_t> sp_gj;                    // [G padded to 8] (group << 4) | element per column, 0xFFFF = takes no part
+    DevBuf<float> sp_ref;                      // [G] reference value per column
+    DevBuf<double> sp_base;                    // one tmp row: the smoothed constant row, filled per smoothing call
+    DevBuf<int64_t> sp_indptr0;                // {0, 0}: the empty row that yields sp_base
     DevBuf<double> c_scratch;  // row pairs with a peak group: third partial sums, [n_sm][2 parities][2 rows][NGpad + PAD_GROUPS]
 
     // ---- direct layout (tier 2); always built
@@ -231,6 +237,16 @@ bool sparse_csr_default() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("ICNV_CSR_SPARSE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// ICNV_CSR_DELTA=0 (developer A/B): CSR input of one-category plans takes the staged-row kernel instead of the delta kernel
+bool sparse_delta_default() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("ICNV_CSR_DELTA");
         v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
@@ -555,6 +571,14 @@ int icnv_plan_create(int device, int32_t n_genes, int32_t n_seg, const int32_t* 
                 p->sp_zrow.alloc((size_t)p->sp_DP))
                 return ICNV_ECUDA;
         }
+        p->delta_ok = p->sparse_ok && sparse_delta_supported(n, gs, p->NGpad, p->n_tasks_g) &&
+                      sparse_delta_smem_bytes(n_genes, p->NGpad, p->qstar >= 0) <= SMEM_MAX;
+        if (p->delta_ok) {
+            const size_t tmp_w = (size_t)((p->n_tasks_g + 31) / 32) * (32 * LOUT + 1);
+            if (p->sp_gj.alloc(((size_t)n_genes + 7) & ~(size_t)7) || p->sp_ref.alloc((size_t)n_genes) || p->sp_base.alloc(tmp_w) ||
+                p->sp_indptr0.upload(std::vector<int64_t>(2, 0)))
+                return ICNV_ECUDA;
+        }
         if (p->permuted && p->qstar >= 0 && p->c_scratch.alloc((size_t)p->n_sm * 8 * (p->NGpad + PAD_GROUPS))) return ICNV_ECUDA;
     }
     if (flat_inv.empty()) flat_inv.push_back(1.0);
@@ -708,6 +732,8 @@ int icnv_plan_set_reference(icnv_plan* plan, const void* ref, int32_t n_cat, int
                 rc = aux_build_bounds(ref, false, n_cat, plan->G, plan->tab[ts].cols_w.ptr, (int64_t)plan->tab[ts].cols_w.n,
                                       plan->tab[ts].lo_w.ptr, plan->tab[ts].hi_w.ptr, false, st);
         if (!rc && plan->sparse_ok) rc = sparse_col_table_launch(ref, false, n_cat, plan->G, plan->sp_col_slot.ptr, plan->sp_col_tab.ptr, st);
+        if (!rc && plan->delta_ok && n_cat == 1)
+            rc = sparse_delta_tables_launch(plan->sp_col_tab.ptr, plan->G, plan->gs, plan->sp_gj.ptr, plan->sp_ref.ptr, st);
     } else {
         rc = aux_build_bounds(ref, c64, n_cat, plan->G, plan->idx_lin.ptr, plan->n_sorted, plan->lo_lin.ptr,
                               plan->hi_lin.ptr, c64, st);
@@ -784,6 +810,18 @@ static int smooth_common(icnv_plan* plan, SmoothParams& sp, double lfc_clip, dou
         rc = sparse_zrow_launch(plan->sp_slot_col.ptr, plan->sp_DP, plan->sp_col_tab.ptr, (float)lfc_clip, plan->bounded, plan->sp_zrow.ptr,
                                 (cudaStream_t)stream);
         if (rc) return rc;
+        if (plan->delta_ok && !plan->bounded && sparse_delta_default()) {
+            // smooth(row) = smooth(constant row) + smooth(deltas of the stored entries): the constant row's result comes from
+            // the staged-row kernel on ONE empty row, the deltas from the entry-proportional kernel
+            rc = sparse_smooth_launch(plan->window, plan->gs, false, plan->sp_indptr0.ptr, sp.indices, sp.data, 1, plan->sp_col_tab.ptr,
+                                      plan->sp_zrow.ptr, plan->sp_DP, plan->NG, plan->NGpad, plan->inv_sumw, plan->flat_inv.ptr,
+                                      plan->tasks_g.ptr, plan->n_tasks_g, (float)lfc_clip, plan->sp_base.ptr, (int64_t)plan->sp_base.n,
+                                      plan->n_sm, (cudaStream_t)stream);
+            if (rc) return rc;
+            return sparse_delta_launch(plan->window, plan->gs, sp.indptr, sp.indices, sp.data, sp.n_rows, plan->sp_gj.ptr, plan->sp_ref.ptr,
+                                       plan->G, plan->NG, plan->NGpad, plan->sp_base.ptr, plan->inv_sumw, plan->flat_inv.ptr,
+                                       plan->tasks_g.ptr, plan->n_tasks_g, (float)lfc_clip, out, ldo, plan->n_sm, (cudaStream_t)stream);
+        }
         return sparse_smooth_launch(plan->window, plan->gs, plan->bounded, sp.indptr, sp.indices, sp.data, sp.n_rows, plan->sp_col_tab.ptr,
                                     plan->sp_zrow.ptr, plan->sp_DP, plan->NG, plan->NGpad, plan->inv_sumw, plan->flat_inv.ptr,
                                     plan->tasks_g.ptr, plan->n_tasks_g, (float)lfc_clip, out, ldo, plan->n_sm, (cudaStream_t)stream);

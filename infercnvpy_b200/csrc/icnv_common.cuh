@@ -22,9 +22,12 @@ __host__ __device__ constexpr int smooth_threads(int rows, bool dbuf = false) { 
 // accumulators per lane instead of 16 + 8.
 #define ICNV_UNIT_WIDTH(rows, peak_group) (((rows) == 2 && !(peak_group)) ? 4 : 2)
 // gather walk of the templated kernels: 0 = conflict-aware permuted walk everywhere (entries carry j / m_j, decoded per
-// entry), 1 = natural walk for windows with a peak group (window 250), 2 = natural walk everywhere
+// entry), 1 = natural walk for windows with a peak group (window 250), 2 = natural walk everywhere.
+// Same-box A/B, 100k x 20k (gpurun_out/r2b/ab_walk.log): window 250 single-row kernel 2.90 ms -> 2.51 ms with the natural
+// walk (the decode of j and m_j costs 8 of ~21 instructions per gene when nothing amortises it), window 100 row pairs
+// 1.865 ms permuted vs 1.90 ms natural -> default 1.
 #ifndef ICNV_NATURAL_WALK
-#define ICNV_NATURAL_WALK 0
+#define ICNV_NATURAL_WALK 1
 #endif
 #ifndef ICNV_LOUT
 #define ICNV_LOUT 9
@@ -256,6 +259,14 @@ int sparse_col_table_launch(const void* ref, bool ref_f64, int n_cat, int G, con
 int sparse_smooth_launch(int nwin, int gs, bool bounded, const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
                          const int4* col_tab, const float* zrow, int DP, int NG, int NGpad, double inv_sumw, const double* flat_inv,
                          const Task* tasks, int n_tasks, float clipf, double* out, int64_t ldo, int n_sm, cudaStream_t st);
+// icnv_sparse_delta.cu: CSR smoothing with work proportional to the stored entries (one category)
+bool sparse_delta_supported(int nwin, int gs, int NGpad, int n_tasks);
+size_t sparse_delta_smem_bytes(int G, int NGpad, bool peak_group);
+int sparse_delta_tables_launch(const int4* col_tab, int G, int gs, uint16_t* gj, float* ref, cudaStream_t st);
+int sparse_delta_launch(int nwin, int gs, const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                        const uint16_t* gj, const float* ref, int G, int NG, int NGpad, const double* base, double inv_sumw,
+                        const double* flat_inv, const Task* tasks, int n_tasks, float clipf, double* out, int64_t ldo, int n_sm,
+                        cudaStream_t st);
 int sparse_colsum_splits(int64_t n_rows, int n_sm);
 int sparse_colsum_launch(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows, int G, const int32_t* row_cat,
                          int n_cat, double* partial, int n_split, cudaStream_t st);
