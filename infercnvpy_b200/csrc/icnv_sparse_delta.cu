@@ -64,8 +64,10 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
     const int ABS = p.NGpad + PAD_GROUPS;
     uint16_t* gj_s = reinterpret_cast<uint16_t*>(smem);
     float* ref_s = reinterpret_cast<float*>(smem + p.Gpad2);
-    int4* AB = reinterpret_cast<int4*>(smem + p.Gpad2 + (size_t)((p.G + 3) & ~3) * 4);  // [2][ABS] {A lo, A hi, B lo, B hi}
-    int2* Cp = reinterpret_cast<int2*>(AB + 2 * ABS);                                     // [2][ABS] {C lo, C hi} (peak-group windows)
+    // limb arrays, structure of arrays so that a warp's scattered adds spread over all 32 banks (bank = group % 32):
+    // L[buffer][limb][group], limbs = {A lo, A hi, B lo, B hi (, C lo, C hi for a window with a peak group)}
+    constexpr int NL = M3_C ? 6 : 4;
+    int* L = reinterpret_cast<int*>(smem + p.Gpad2 + (size_t)((p.G + 3) & ~3) * 4);
 
     const int lane = threadIdx.x & 31;
     const int warp = DW - 1 - (int)(threadIdx.x >> 5);  // consumers take the highest physical warp ids
@@ -80,10 +82,8 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
         uint4* d4 = reinterpret_cast<uint4*>(gj_s);
         for (int i = threadIdx.x; i < p.Gpad2 / 16; i += DT) d4[i] = __ldg(g4 + i);
         for (int i = threadIdx.x; i < p.G; i += DT) ref_s[i] = __ldg(p.ref + i);
-        for (int i = threadIdx.x; i < 2 * ABS; i += DT) {
-            AB[i] = make_int4(0, 0, 0, 0);
-            if (M3_C) Cp[i] = make_int2(0, 0);
-        }
+        int4* L4 = reinterpret_cast<int4*>(L);
+        for (int i = threadIdx.x; i < 2 * NL * ABS / 4; i += DT) L4[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
 
@@ -101,19 +101,21 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
             const int b = (int)(it & 1);
             const int64_t e0 = __ldg(p.indptr + row);
             const int nnz = (int)(__ldg(p.indptr + row + 1) - e0);
-            const int32_t* ip = p.indices + e0;
-            const float* vp = p.data + e0;
-            int4* ABb = AB + b * ABS;
-            int2* Cb = Cp + b * ABS;
+            const int32_t* ip = p.indices + e0 + pt;
+            const float* vp = p.data + e0 + pt;
+            int* Lb = L + b * NL * ABS;
             int c[U];
             float v[U];
-            int e = pt;
+            int left = nnz - pt;  // entries from this thread's first one to the end of the row
             auto load = [&]() {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const bool ok = e + u * n_prod < nnz;
-                    c[u] = ok ? __ldg(ip + e + u * n_prod) : -1;
-                    v[u] = ok ? ldg_stream_f32(vp + e + u * n_prod) : 0.f;
+                    c[u] = -1;
+                    v[u] = 0.f;
+                    if (u * n_prod < left) {
+                        c[u] = __ldg(ip + u * n_prod);
+                        v[u] = ldg_stream_f32(vp + u * n_prod);
+                    }
                 }
             };
             load();  // in flight while the buffer is still being read by the consumers
@@ -130,37 +132,39 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
             while (true) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (c[u] < 0) continue;
-                    const uint32_t gjv = gj_s[c[u]];
-                    if (gjv == 0xFFFFu) continue;
-                    const float r = ref_s[c[u]];
+                    const int cc = c[u] < 0 ? 0 : c[u];
+                    const uint32_t gjv = gj_s[cc];
+                    const float r = ref_s[cc];
+                    const bool act = c[u] >= 0 && gjv != 0xFFFFu;
                     const float d = fminf(fmaxf(v[u] - r, -clipf), clipf);
-                    const float z = fminf(fmaxf(0.f - r, -clipf), clipf);
+                    const float z = fminf(fmaxf(-r, -clipf), clipf);
                     const long long dfx = __float2ll_rn(d * 281474976710656.0f) - __float2ll_rn(z * 281474976710656.0f);
-                    if (dfx == 0) continue;
                     const int g = (int)(gjv >> 4), j = (int)(gjv & 15u);
-                    int* slot = reinterpret_cast<int*>(ABb + g);
-                    atomicAdd(slot + 0, (int)(dfx & ((1ll << LIMB) - 1)));
-                    atomicAdd(slot + 1, (int)(dfx >> LIMB));
-                    if (j != 0) {
-                        const long long bfx = dfx * j;
-                        atomicAdd(slot + 2, (int)(bfx & ((1ll << LIMB) - 1)));
-                        atomicAdd(slot + 3, (int)(bfx >> LIMB));
-                    }
-                    if constexpr (M3_C) {
-                        // non-linear part of the peak group's weights: m_j = w(q*, j) - w(q*, 0)
-                        const int pk = (NWIN / 2) - GS * (M3_C ? QSTAR_C : 0);  // elements before the peak inside the group
-                        const int m = j < pk ? j : 2 * pk - 1 - j;
-                        if (m != 0) {
-                            const long long cfx = dfx * m;
-                            int* cs = reinterpret_cast<int*>(Cb + g);
-                            atomicAdd(cs + 0, (int)(cfx & ((1ll << LIMB) - 1)));
-                            atomicAdd(cs + 1, (int)(cfx >> LIMB));
+                    const long long bfx = dfx * j;
+                    int* slot = Lb + g;
+                    if (act) {
+                        atomicAdd(slot, (int)((unsigned)dfx & ((1u << LIMB) - 1u)));
+                        atomicAdd(slot + ABS, (int)(dfx >> LIMB));
+                        if (j != 0) {
+                            atomicAdd(slot + 2 * ABS, (int)((unsigned)bfx & ((1u << LIMB) - 1u)));
+                            atomicAdd(slot + 3 * ABS, (int)(bfx >> LIMB));
+                        }
+                        if constexpr (M3_C) {
+                            // non-linear part of the peak group's weights: m_j = w(q*, j) - w(q*, 0)
+                            const int pk = (NWIN / 2) - GS * (M3_C ? QSTAR_C : 0);  // elements before the peak inside the group
+                            const int m = j < pk ? j : 2 * pk - 1 - j;
+                            if (m != 0) {
+                                const long long cfx = dfx * m;
+                                atomicAdd(slot + 4 * ABS, (int)((unsigned)cfx & ((1u << LIMB) - 1u)));
+                                atomicAdd(slot + 5 * ABS, (int)(cfx >> LIMB));
+                            }
                         }
                     }
                 }
-                e += U * n_prod;
-                if (e - pt >= nnz) break;  // uniform per CTA: every producer leaves after the same batch
+                left -= U * n_prod;
+                if (left + pt <= 0) break;  // the row is exhausted for every producer at the same batch
+                ip += U * n_prod;
+                vp += U * n_prod;
                 load();
             }
             named_bar_arrive(BAR_FULL + b, DT);
@@ -176,8 +180,7 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
     for (int64_t it = 0; it < n_it; ++it) {
         const int64_t row = first + it * gridDim.x;
         const int b = (int)(it & 1);
-        const int4* ABb = AB + b * ABS;
-        const int2* Cb = Cp + b * ABS;
+        int* Lb = L + b * NL * ABS;
         named_bar_sync(BAR_FULL + b, DT);  // every entry of the row has been added
         double v[LOUT];
         int nv = 0;
@@ -188,11 +191,10 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
             const int4 t = task;
             if ((t.w & 0xFF) == 0) {
                 nv = t.z;
-                const int4* P = ABb + t.x;
+                const int* P = Lb + t.x;
 #pragma unroll
                 for (int q = 0; q < NQ_C + LOUT - 1; ++q) {
-                    const int4 ab = P[q];
-                    const double A = limbs_to_double(ab.x, ab.y), B = limbs_to_double(ab.z, ab.w);
+                    const double A = limbs_to_double(P[q], P[q + ABS]), B = limbs_to_double(P[q + 2 * ABS], P[q + 3 * ABS]);
 #pragma unroll
                     for (int i = 0; i < LOUT; ++i) {
                         const int w = q - i;
@@ -210,29 +212,21 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
                 if constexpr (M3_C) {
 #pragma unroll
                     for (int i = 0; i < LOUT; ++i) {
-                        const int2 c2 = Cb[t.x + QSTAR_C + i];
-                        v[i] += limbs_to_double(c2.x, c2.y);
+                        v[i] += limbs_to_double(P[QSTAR_C + i + 4 * ABS], P[QSTAR_C + i + 5 * ABS]);
                     }
                 }
             } else {
                 nv = 1;  // chromosome not longer than the window: one flat mean (_infercnv.py:227-236)
                 double acc = 0.0;
-                for (int g = 0; g < t.z; ++g) {
-                    const int4 ab = ABb[t.x + g];
-                    acc += limbs_to_double(ab.x, ab.y);
-                }
+                for (int g = 0; g < t.z; ++g) acc += limbs_to_double(Lb[t.x + g], Lb[t.x + g + ABS]);
                 v[0] = acc;
                 scale = p.fx_inv * p.flat_inv[t.w >> 8];
             }
         }
         named_bar_sync(BAR_CONS, n_cons);  // every consumer has read its partial sums
         {
-            int4* Z = AB + b * ABS;
-            int2* ZC = Cp + b * ABS;
-            for (int i = tid; i < ABS; i += n_cons) {
-                Z[i] = make_int4(0, 0, 0, 0);
-                if (M3_C) ZC[i] = make_int2(0, 0);
-            }
+            int4* Z = reinterpret_cast<int4*>(Lb);
+            for (int i = tid; i < NL * ABS / 4; i += n_cons) Z[i] = make_int4(0, 0, 0, 0);
         }
         if (it + 2 < n_it) named_bar_arrive(BAR_FREE + b, DT);  // matched by the producers' wait two rows from now
         // ---- base + delta, tile moments, tile-order float64 row (layout of SmoothParams::out)
