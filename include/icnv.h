@@ -234,6 +234,24 @@ double icnv_host_schedule_gathers(const int32_t* gcol, int32_t n_groups, int32_t
  * [grid][rows_per_cta][16] for the first rows_per_cta rows of every CTA.  NULL switches it off. */
 int icnv_debug_set_timeline(long long* dev_buf, int rows_per_cta);
 
+/* ------------------------------------------------------------- embeddings ----
+ * cnv.tl.umap / cnv.tl.tsne (tl/__init__.py:78-144: wrappers around scanpy.tl.umap / scanpy.tl.tsne; parity unpinned).
+ * icnv_umap_epochs: epochs [epoch0, epoch0 + n_run) of umap-learn's optimize_layout_euclidean on a 2-D embedding
+ *   emb [n_vertices, 2] float32 (updated in place).  head / tail [n_edges] int32: the directed edges of the symmetric
+ *   graph; epochs_per_sample [n_edges] = max weight / weight; next_sample / next_negative [n_edges] are the per-edge
+ *   schedules (initialise to epochs_per_sample and epochs_per_sample / neg_rate; carried between calls).
+ * icnv_tsne_affinities: joint probabilities P [n, n] float32 of exact t-SNE from X [n, d <= 64] (per-row perplexity
+ *   search, symmetrised, floor 1e-12).
+ * icnv_tsne_iterations: n_iter gradient-descent steps (scikit-learn's gains / momentum rule) on Y [n, 2]; vel, gains
+ *   [n, 2] carried between calls; work: icnv_tsne_work_floats(n) floats. */
+int icnv_umap_epochs(const int32_t* head, const int32_t* tail, int64_t n_edges, float* emb, int32_t n_vertices,
+                     const float* epochs_per_sample, float* next_sample, float* next_negative, float a, float b, float gamma,
+                     float alpha0, int32_t n_epochs, int32_t epoch0, int32_t n_run, int32_t neg_rate, uint32_t seed, void* stream);
+int icnv_tsne_affinities(const float* X, int32_t n, int32_t d, int64_t ld, float perplexity, float* P, void* stream);
+int64_t icnv_tsne_work_floats(int32_t n);
+int icnv_tsne_iterations(const float* P, float* Y, float* vel, float* gains, float* work, int32_t n, int32_t n_iter,
+                         float exaggeration, float momentum, float learning_rate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

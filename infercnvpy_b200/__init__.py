@@ -7,9 +7,9 @@
 Reference namespace layout: ``/root/reference/src/infercnvpy/__init__.py:3-8``.
 """
 
-from . import datasets, pl, pp, tl
+from . import datasets, io, pl, pp, tl
 from ._anndata import AnnData
 from ._layout import build_layout, shard_rows
 
 __version__ = "0.1.0"
-__all__ = ["tl", "pp", "pl", "datasets", "AnnData", "build_layout", "shard_rows"]
+__all__ = ["tl", "pp", "pl", "io", "datasets", "AnnData", "build_layout", "shard_rows"]

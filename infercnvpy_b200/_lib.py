@@ -56,6 +56,11 @@ SIGNATURES = {
     "icnv_weighted_degree": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, c_vp]),
     "icnv_community_sweep_work_bytes": (C.c_int64, [C.c_int64]),
     "icnv_community_sweep": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, C.c_double, C.c_double, C.c_int32, c_vp, c_vp, c_vp, c_vp]),
+    "icnv_umap_epochs": (C.c_int, [c_vp, c_vp, C.c_int64, c_vp, C.c_int32, c_vp, c_vp, c_vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, c_vp]),
+    "icnv_tsne_affinities": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int64, C.c_float, c_vp, c_vp]),
+    "icnv_tsne_work_floats": (C.c_int64, [C.c_int32]),
+    "icnv_tsne_iterations": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, c_vp]),
     "icnv_host_schedule_gathers": (C.c_double, [c_i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_i32p, C.POINTER(C.c_uint8)]),
     "icnv_debug_set_timeline": (C.c_int, [c_vp, C.c_int]),
     "icnv_label_sums": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int32, c_vp, c_vp, c_vp]),

@@ -28,6 +28,10 @@ int aux_build_bounds(const void*, bool, int, int, const int32_t*, int64_t, void*
 int aux_chunk_threshold(const double*, int64_t, int64_t, int64_t, double, double*, cudaStream_t);
 int aux_center_rows(const double*, int64_t, int64_t, const Task*, int, int, void*, bool, int64_t, double*, cudaStream_t);
 int aux_apply_threshold(void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
+int umap_epochs(const int32_t*, const int32_t*, int64_t, float*, int32_t, const float*, float*, float*, float, float, float, float, int, int,
+                int, int, uint32_t, cudaStream_t);
+int tsne_affinities(const float*, int, int, int64_t, float, float*, cudaStream_t);
+int tsne_iterations(const float*, float*, float*, float*, float*, int, int, float, float, float, cudaStream_t);
 int filter_count(const void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, double*, int32_t*, cudaStream_t);
 int filter_to_csr(const void*, bool, int64_t, int64_t, int64_t, int64_t, const double*, const int64_t*, int32_t*, void*, bool, cudaStream_t);
 int smooth_raw_base(uint32_t* base);
@@ -1122,6 +1126,34 @@ int icnv_community_sweep(const int64_t* indptr, const int32_t* indices, const fl
         return ICNV_EINVAL;
     }
     return graph_community_sweep(indptr, indices, w, kdeg, comm, bound, n, two_m, gamma, sweep, work, comm_new, stats, (cudaStream_t)stream);
+}
+
+int icnv_umap_epochs(const int32_t* head, const int32_t* tail, int64_t n_edges, float* emb, int32_t n_vertices,
+                     const float* epochs_per_sample, float* next_sample, float* next_negative, float a, float b, float gamma,
+                     float alpha0, int32_t n_epochs, int32_t epoch0, int32_t n_run, int32_t neg_rate, uint32_t seed, void* stream) {
+    if (n_edges < 0 || n_vertices < 1 || n_epochs < 1 || neg_rate < 1 || !emb ||
+        (n_edges > 0 && (!head || !tail || !epochs_per_sample || !next_sample || !next_negative))) {
+        set_error("icnv_umap_epochs: bad argument");
+        return ICNV_EINVAL;
+    }
+    return umap_epochs(head, tail, n_edges, emb, n_vertices, epochs_per_sample, next_sample, next_negative, a, b, gamma, alpha0, n_epochs,
+                       epoch0, n_run, neg_rate, seed, (cudaStream_t)stream);
+}
+int icnv_tsne_affinities(const float* X, int32_t n, int32_t d, int64_t ld, float perplexity, float* P, void* stream) {
+    if (!X || !P || n < 2 || d < 1 || d > 64 || ld < d || !(perplexity > 0.f) || perplexity >= (float)n) {
+        set_error("icnv_tsne_affinities: bad argument (2 <= n, 1 <= d <= 64, 0 < perplexity < n)");
+        return ICNV_EINVAL;
+    }
+    return tsne_affinities(X, n, d, ld, perplexity, P, (cudaStream_t)stream);
+}
+int64_t icnv_tsne_work_floats(int32_t n) { return n < 0 ? -1 : 5 * (int64_t)n + 4; }
+int icnv_tsne_iterations(const float* P, float* Y, float* vel, float* gains, float* work, int32_t n, int32_t n_iter, float exaggeration,
+                         float momentum, float learning_rate, void* stream) {
+    if (!P || !Y || !vel || !gains || !work || n < 2 || n_iter < 0) {
+        set_error("icnv_tsne_iterations: bad argument");
+        return ICNV_EINVAL;
+    }
+    return tsne_iterations(P, Y, vel, gains, work, n, n_iter, exaggeration, momentum, learning_rate, (cudaStream_t)stream);
 }
 
 }  // extern "C"

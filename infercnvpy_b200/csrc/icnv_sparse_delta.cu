@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(DT, 1) smooth_csr_delta_kernel(const DeltaPara
             while (true) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
+                    if (u * n_prod >= left + lane) continue;  // warp-uniform: none of the warp's 32 slots holds an entry
                     const int cc = c[u] < 0 ? 0 : c[u];
                     const uint32_t gjv = gj_s[cc];
                     const float r = ref_s[cc];

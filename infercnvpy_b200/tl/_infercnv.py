@@ -38,6 +38,10 @@ def _rows_to_device(expr, r0, r1, device):
     """Rows [r0, r1) of the host matrix as device float32 (dense tensor or CSR triple)."""
     import torch
 
+    from ..io import DeviceCSR
+
+    if isinstance(expr, DeviceCSR):  # already in HBM (infercnvpy_b200.io.read_matrix): canonical CSR, views only
+        return expr.rows(r0, r1)
     if scipy.sparse.issparse(expr):
         whole = r0 == 0 and r1 == expr.shape[0] and expr.format == "csr"
         blk = expr if whole else expr[r0:r1].tocsr()
@@ -287,7 +291,9 @@ def _cached_plan(var, window_size, step, exclude_chromosomes, device):
     import hashlib
 
     h = hashlib.sha1()
-    h.update("\x00".join(map(str, var["chromosome"].astype(str))).encode("utf-8"))
+    import pandas as pd
+
+    h.update(pd.util.hash_pandas_object(var["chromosome"], index=False).to_numpy().tobytes())  # vectorised, 64 bits per gene
     h.update(np.ascontiguousarray(np.asarray(var["start"], dtype=np.float64)).tobytes())
     key = (h.hexdigest(), int(window_size), int(step), None if exclude_chromosomes is None else tuple(exclude_chromosomes), str(device))
     hit = _PLAN_CACHE.get(key)

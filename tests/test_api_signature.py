@@ -22,6 +22,8 @@ CASES = [
     ("tl/__init__.py", "pca", cnv.tl.pca),
     ("tl/__init__.py", "leiden", cnv.tl.leiden),
     ("pp/__init__.py", "neighbors", cnv.pp.neighbors),
+    ("tl/__init__.py", "umap", cnv.tl.umap),
+    ("tl/__init__.py", "tsne", cnv.tl.tsne),
 ]
 
 

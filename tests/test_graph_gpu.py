@@ -227,3 +227,80 @@ def test_leiden_and_workflow(clones):
     assert score["k0"] < score["k1"] and score["k0"] < score["k2"]
     res = cnv.tl.leiden(adata, inplace=False, resolution=0.5)
     assert len(res.categories) <= len(lab.cat.categories)
+
+
+def _knn_purity(emb, labels, k=10):
+    from sklearn.neighbors import NearestNeighbors
+
+    idx = NearestNeighbors(n_neighbors=k + 1).fit(emb).kneighbors(emb, return_distance=False)[:, 1:]
+    return float((labels[idx] == labels[:, None]).mean())
+
+
+def test_umap_and_tsne_embeddings(clones):
+    """/root/reference/src/infercnvpy/tl/__init__.py:78-144 (wrappers around scanpy.tl.umap / scanpy.tl.tsne; the
+    reference's test_workflow asserts nothing).  Ours: keys / shapes like the reference, the local structure of the PCA
+    space survives (scikit-learn trustworthiness) and the planted clones stay apart in the plane."""
+    from sklearn.manifold import trustworthiness
+
+    adata, clone = clones
+    if "cnv_neighbors" not in adata.uns:
+        cnv.tl.pca(adata)
+        cnv.pp.neighbors(adata)
+    Y = np.asarray(adata.obsm["X_cnv_pca"])
+    cnv.tl.umap(adata)
+    U = adata.obsm["X_cnv_umap"]
+    assert U.shape == (adata.n_obs, 2) and U.dtype == np.float32 and np.isfinite(U).all()
+    tw_u, pur_u = trustworthiness(Y, U, n_neighbors=15), _knn_purity(U, clone)
+    # deterministic schedule and hash-based negative samples, float atomics: repeat runs agree up to summation order
+    U2 = cnv.tl.umap(adata, inplace=False)
+    assert U2.shape == U.shape and _knn_purity(U2, clone) > 0.95
+    V = cnv.tl.umap(adata, inplace=False, init_pos="random", min_dist=0.1, maxiter=100)
+    assert np.isfinite(V).all() and _knn_purity(V, clone) > 0.9
+    with pytest.raises(TypeError):
+        cnv.tl.umap(adata, n_components=3)
+    cnv.tl.tsne(adata)
+    T = adata.obsm["X_cnv_tsne"]
+    assert T.shape == (adata.n_obs, 2) and np.isfinite(T).all()
+    tw_t, pur_t = trustworthiness(Y, T, n_neighbors=15), _knn_purity(T, clone)
+    print(f"\n[embeddings] umap trustworthiness {tw_u:.3f}, clone purity {pur_u:.3f}; tsne {tw_t:.3f}, {pur_t:.3f}")
+    assert tw_u > 0.80 and pur_u > 0.95
+    assert tw_t > 0.90 and pur_t > 0.95
+    with pytest.raises(ValueError, match="perplexity"):
+        cnv.tl.tsne(adata, perplexity=1e9)
+
+
+def test_tsne_affinities_match_numpy_restatement():
+    """Conditional probabilities of the requested perplexity, symmetrised (scikit-learn's _joint_probabilities)."""
+    import torch
+
+    from infercnvpy_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(300, 7)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    Xd = torch.from_numpy(X).to(dev)
+    P = torch.empty((300, 300), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.icnv_tsne_affinities(_lib.ptr(Xd), 300, 7, 7, 20.0, _lib.ptr(P), _lib.stream_handle(dev)), "icnv_tsne_affinities")
+    P = P.cpu().numpy().astype(np.float64)
+    assert np.allclose(P, P.T) and abs(P.sum() - 1.0) < 1e-4 and (np.diag(P) == 0).all()
+    # numpy restatement: per-row bisection on beta to entropy log(perplexity)
+    D = ((X[:, None, :].astype(np.float64) - X[None, :, :]) ** 2).sum(-1)
+    C = np.zeros_like(D)
+    for i in range(300):
+        lo, hi, beta = -np.inf, np.inf, 1.0
+        d = np.delete(D[i], i)
+        for _ in range(200):
+            p = np.exp(-d * beta)
+            s = p.sum()
+            H = np.log(s) + beta * (d * p).sum() / s
+            if abs(H - np.log(20.0)) < 1e-7:
+                break
+            if H > np.log(20.0):
+                lo, beta = beta, beta * 2 if np.isinf(hi) else (beta + hi) / 2
+            else:
+                hi, beta = beta, beta / 2 if np.isinf(lo) else (beta + lo) / 2
+        C[i, np.arange(300) != i] = p / s
+    want = np.maximum((C + C.T) / 600.0, 1e-12)
+    np.fill_diagonal(want, 0.0)
+    np.testing.assert_allclose(P, want, rtol=2e-3, atol=1e-9)
