@@ -189,7 +189,7 @@ class ClockSampler:
         self.thread.start()
 
     def stop(self):
-        if self.nv is None:
+        if self.nv is None or self.thread is None:  # never started (ranks other than 0 do not sample)
             return
         self.stop_flag.set()
         self.thread.join(timeout=1)
