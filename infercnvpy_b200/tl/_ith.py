@@ -3,8 +3,9 @@
 
 Per group of cells: Pearson correlation of every pair of cells (``np.corrcoef`` over rows, ``:136,209``), score =
 inter-quartile range of ALL entries of that cells x cells matrix (``np.percentile(pcorr, [75, 25])``, ``:141,214``).
-The correlation matrix is built by ``icnv_row_corrcoef_f64`` (fp64 tiles on the GPU); the two quartiles are read off a
-device sort of its entries with numpy's linear-interpolation rule.  Groups do not shard: every rank scores the cells
+The correlation matrix is built by ``icnv_row_corrcoef_f64`` (fp64 tiles on the GPU); the two quartiles are exact
+order statistics (numpy's linear-interpolation rule) found by a sample-bracketed selection instead of a sort of the
+``n_g^2`` entries, so a group is limited by its correlation matrix alone (~130k cells on a 180 GB GPU).  Groups do not shard: every rank scores the cells
 it holds ("replicas only").
 """
 
@@ -19,21 +20,58 @@ import scipy.sparse as sp
 from .. import _lib
 
 
-def _np_linear_quantile(sorted_flat, n_total: int, q: float) -> float:
-    """numpy's default ('linear') percentile on an ascending device vector: virtual index ``q * (N - 1)`` computed like
-    ``numpy.lib._function_base_impl._compute_virtual_index`` (alpha = beta = 1), value by numpy's ``_lerp``."""
-    vi = n_total * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0
-    lo = int(math.floor(vi))
-    lo = min(max(lo, 0), n_total - 1)
-    hi = min(lo + 1, n_total - 1)
-    g = vi - math.floor(vi)
-    a = float(sorted_flat[lo].item())
-    b = float(sorted_flat[hi].item())
+def _lerp_np(a: float, b: float, g: float) -> float:
+    """numpy's ``_lerp`` (``numpy/lib/_function_base_impl.py``): ``a + (b - a) * g``, evaluated from ``b`` when ``g >= 0.5``."""
     diff = b - a
     val = a + diff * g
     if g >= 0.5:
         val = b - diff * (1.0 - g)
     return val
+
+
+def _virtual_index(n_total: int, q: float):
+    """numpy's default ('linear') percentile: virtual index ``q * (N - 1)`` computed like ``_compute_virtual_index``
+    (alpha = beta = 1) -> (lower order statistic, upper order statistic, interpolation weight)."""
+    vi = n_total * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0
+    lo = min(max(int(math.floor(vi)), 0), n_total - 1)
+    hi = min(lo + 1, n_total - 1)
+    return lo, hi, vi - math.floor(vi)
+
+
+def _order_statistics(flat, ranks, panel: int = 1 << 26):
+    """Exact order statistics ``sorted(flat)[r] for r in ranks`` of a device float64 vector WITHOUT sorting it (a sort
+    needs two more copies of the n_g^2 correlations).  A strided sample brackets every rank; one counting pass gives the
+    number of values below the bracket, one gathering pass its members (a few thousand), which are sorted exactly.  A
+    bracket that misses its rank (cannot happen for a consistent sample, but ties can crowd it) is widened and retried."""
+    import torch
+
+    n = flat.numel()
+    stride = max(1, n // (1 << 20))
+    sample = torch.sort(flat[::stride]).values
+    m = sample.numel()
+    out = {}
+    for r in sorted(set(ranks)):
+        pos = r / max(1, n - 1) * (m - 1)
+        margin = max(8.0, 6.0 * math.sqrt(m))  # ~6 sigma of the sample rank
+        for _attempt in range(8):
+            i0, i1 = int(max(0, math.floor(pos - margin))), int(min(m - 1, math.ceil(pos + margin)))
+            a = float(sample[i0].item()) if i0 > 0 else -math.inf
+            b = float(sample[i1].item()) if i1 < m - 1 else math.inf
+            below = 0
+            parts = []
+            for p0 in range(0, n, panel):
+                x = flat[p0 : p0 + panel]
+                below += int((x < a).sum().item())
+                parts.append(x[(x >= a) & (x <= b)])
+            cand = torch.cat(parts)
+            k = r - below
+            if 0 <= k < cand.numel() and cand.numel() <= (1 << 27):
+                out[r] = float(torch.sort(cand).values[k].item())
+                break
+            margin *= 4.0
+        else:  # pragma: no cover
+            raise _lib.IcnvError("ITH: quantile bracket did not converge")
+    return [out[r] for r in ranks]
 
 
 def _group_iqr(block: np.ndarray, device) -> float:
@@ -43,10 +81,10 @@ def _group_iqr(block: np.ndarray, device) -> float:
     lib = _lib.load()
     n, K = block.shape
     free, _ = torch.cuda.mem_get_info(device)
-    need = 3 * 8 * n * n + 8 * n * K
+    need = 8 * n * n + 8 * n * K + (3 << 30)  # the matrix, the block, selection scratch (no sort of the n_g^2 entries)
     if need > free:
         raise _lib.IcnvError(
-            f"group of {n} cells needs {need / 2**30:.1f} GiB for its correlation matrix and the sort; "
+            f"group of {n} cells needs {need / 2**30:.1f} GiB for its correlation matrix; "
             f"{free / 2**30:.1f} GiB are free on {device}"
         )
     X = torch.from_numpy(np.ascontiguousarray(block, dtype=np.float64)).to(device)
@@ -56,13 +94,21 @@ def _group_iqr(block: np.ndarray, device) -> float:
         lib.icnv_row_corrcoef_f64(_lib.ptr(X), n, X.stride(0), K, _lib.ptr(corr), corr.stride(0), _lib.ptr(work), _lib.stream_handle(device)),
         "icnv_row_corrcoef_f64",
     )
-    if bool(torch.isnan(corr).any().item()):  # np.percentile of an array with a NaN is NaN
-        return float("nan")
-    flat = torch.sort(corr.reshape(-1)).values
-    del corr
-    q75 = _np_linear_quantile(flat, n * n, 0.75)
-    q25 = _np_linear_quantile(flat, n * n, 0.25)
-    return q75 - q25
+    del X
+    flat = corr.reshape(-1)
+    panel = 1 << 26
+    for p0 in range(0, flat.numel(), panel):  # np.percentile of an array with a NaN is NaN
+        if bool(torch.isnan(flat[p0 : p0 + panel]).any().item()):
+            return float("nan")
+    N = n * n
+    if N <= (1 << 22):  # small groups: a plain sort is cheaper than the selection passes
+        srt = torch.sort(flat).values
+        pick = lambda r: float(srt[r].item())  # noqa: E731
+        (l75, h75, g75), (l25, h25, g25) = _virtual_index(N, 0.75), _virtual_index(N, 0.25)
+        return _lerp_np(pick(l75), pick(h75), g75) - _lerp_np(pick(l25), pick(h25), g25)
+    (l75, h75, g75), (l25, h25, g25) = _virtual_index(N, 0.75), _virtual_index(N, 0.25)
+    a75, b75, a25, b25 = _order_statistics(flat, [l75, h75, l25, h25])
+    return _lerp_np(a75, b75, g75) - _lerp_np(a25, b25, g25)
 
 
 def _ith(adata, groupby: str, get_block) -> dict:

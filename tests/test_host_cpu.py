@@ -142,24 +142,34 @@ def test_gather_schedule_invariants(g, sort_in_memory):
 
 
 def test_quantile_rule_matches_numpy_percentile():
-    """tl/_ith.py reads the quartiles of the sorted correlation entries with numpy's default ('linear') rule
-    (_scores.py:141,214 call np.percentile(pcorr, [75, 25]))."""
+    """tl/_ith.py takes the quartiles of the correlation entries with numpy's default ('linear') rule
+    (_scores.py:141,214 call np.percentile(pcorr, [75, 25])): virtual index + _lerp on exact order statistics, which come
+    from a sort (small groups) or from the sample-bracketed selection (large groups) -- both checked here on CPU tensors."""
     import torch
 
-    from infercnvpy_b200.tl._ith import _np_linear_quantile
+    from infercnvpy_b200.tl._ith import _lerp_np, _order_statistics, _virtual_index
+
+    def quantile(a_sorted, q):
+        lo, hi, g = _virtual_index(a_sorted.size, q)
+        return _lerp_np(float(a_sorted[lo]), float(a_sorted[hi]), g)
 
     rng = np.random.default_rng(3)
     for n in (1, 2, 3, 4, 5, 9, 16, 25, 1000, 4097):
         a = np.sort(rng.normal(size=n))
-        t = torch.from_numpy(a)
         for q in (0.25, 0.75):
-            assert _np_linear_quantile(t, n, q) == float(np.percentile(a, 100 * q)), (n, q)
+            assert quantile(a, q) == float(np.percentile(a, 100 * q)), (n, q)
     # ties and a constant vector
     a = np.sort(np.repeat(rng.normal(size=7), 5))
     for q in (0.25, 0.75):
-        assert _np_linear_quantile(torch.from_numpy(a), a.size, q) == float(np.percentile(a, 100 * q))
-    ones = torch.ones(36, dtype=torch.float64)
-    assert _np_linear_quantile(ones, 36, 0.75) - _np_linear_quantile(ones, 36, 0.25) == 0.0
+        assert quantile(a, q) == float(np.percentile(a, 100 * q))
+    assert quantile(np.ones(36), 0.75) - quantile(np.ones(36), 0.25) == 0.0
+    # selection without a full sort: exact order statistics on unsorted data, heavy ties, tiny panels
+    for data in (rng.normal(size=300_001), np.round(rng.normal(size=200_000), 1), np.ones(70_000), np.clip(rng.normal(size=150_000), -0.3, 0.3)):
+        t = torch.from_numpy(data.copy())
+        srt = np.sort(data)
+        ranks = [0, 1, data.size // 4, data.size // 4 + 1, (3 * data.size) // 4, data.size - 1]
+        got = _order_statistics(t, ranks, panel=1 << 16)
+        assert got == [float(srt[r]) for r in ranks]
 
 
 def test_block_rows_are_multiples_of_chunksize(monkeypatch):
@@ -264,3 +274,17 @@ def test_io_opens_npy_npz_and_csr_directory(tmp_path):
     chr_pos, back = cio.read_cnv(tmp_path / "cnv.npz")
     assert chr_pos == {"chr1": 0, "chr2": 17} and (back != A).nnz == 0 and back.dtype == np.float64
     assert (sp.load_npz(tmp_path / "cnv.npz") != A).nnz == 0
+
+
+def test_bench_clock_sampler_stop_without_start():
+    """Ranks other than 0 construct the sampler but never start it; stop() must be a no-op there (a crash after the
+    JSON line makes torchrun report the whole bench as failed)."""
+    import importlib.util
+    import threading
+
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.nv, s.thread, s.stop_flag, s.samples, s.period, s.max_mhz = object(), None, threading.Event(), [], 0.004, None
+    s.stop()

@@ -682,6 +682,15 @@ def test_ith_scores_known_answers_and_golden():
         assert np.isnan(res[k]) == np.isnan(want[k])
         if not np.isnan(want[k]):
             assert float(res[k]) == pytest.approx(float(want[k]), rel=1e-9)
+    # a group above 2048 cells takes the selection path (no sort of the n_g^2 correlations): same numbers as numpy
+    rng = np.random.default_rng(11)
+    big = (rng.normal(size=(2600, 90)) + rng.normal(size=(1, 90)) * 0.7).astype(np.float64)
+    lab = np.where(np.arange(2600) < 2500, "big", "small")
+    c = cnv.AnnData(big, obs=pd.DataFrame({"g": lab}, index=[f"c{i}" for i in range(2600)]))
+    got = cnv.tl.ithgex(c, "g", inplace=False)
+    want = orc.ith_score(big, lab)
+    for k in want:
+        assert float(got[k]) == pytest.approx(float(want[k]), rel=1e-9), k
 
 
 def test_group_means_match_numpy(golden_loader):
@@ -745,3 +754,37 @@ def test_disk_to_hbm_loader_shards_and_feeds_infercnv(tmp_path):
     _, want_d, _ = cnv.tl.infercnv(_adata(X, var), **kw)
     _, got_d, _ = cnv.tl.infercnv(_adata(Xd, var), **kw)
     assert (got_d != want_d).nnz == 0
+
+
+def test_edge_cases_empty_ragged_and_degenerate_rows():
+    """Empty and ragged inputs through the public API against the oracle: no cells, one cell, a chunk size larger than
+    the matrix, CSR rows without any stored entry, a fully dense CSR row, explicitly stored zeros."""
+    var = cnv.datasets.synthetic_var(2400, seed=0, with_extras=True)
+    chrom, start = var["chromosome"].values, var["start"].values
+    X = cnv.datasets.synthetic_counts(23, 2400, seed=77)
+    ref = X.mean(axis=0, dtype=np.float64).astype(np.float32)
+    # no cells: the reference's process_map gets no chunk and vstack fails; here an empty CSR of the right width
+    for empty in (X[:0], sp.csr_matrix(X[:0])):
+        chr_pos, res, _ = cnv.tl.infercnv(_adata(empty, var), reference=ref, inplace=False)
+        assert res.shape[0] == 0 and res.shape[1] > 0 and res.nnz == 0 and list(chr_pos)[0] == "chr1"
+    # one cell / chunksize larger than the matrix / ragged last chunk
+    for n, chunk in ((1, 5000), (23, 5000), (23, 7)):
+        chr_pos_o, want = orc.infercnv(X[:n], chrom, start, reference=ref, chunksize=chunk)[:2]
+        for Xin in (X[:n], sp.csr_matrix(X[:n])):
+            chr_pos, res, _ = cnv.tl.infercnv(_adata(Xin, var), reference=ref, chunksize=chunk, inplace=False)
+            assert {k: int(v) for k, v in chr_pos.items()} == {k: int(v) for k, v in chr_pos_o.items()}
+            _compare_thresholded(res.toarray(), want.toarray(), chunk, what=f"n={n} chunk={chunk}", max_flips=2)
+    # CSR with empty rows, one fully dense row and explicitly stored zeros
+    Y = X.copy()
+    Y[3] = 0.0
+    Y[11] = 0.0
+    Y[5] = np.float32(0.5) + Y[5]
+    S = sp.csr_matrix(Y)
+    S.data[::17] = 0.0  # stored zeros (the dense twin gets the same zeros)
+    Yd = S.toarray()
+    assert S.nnz > (Yd != 0).sum()
+    _, want = orc.infercnv(Yd, chrom, start, reference=ref, chunksize=10)[:2]
+    _, got_s, _ = cnv.tl.infercnv(_adata(S, var), reference=ref, chunksize=10, inplace=False)
+    _, got_d, _ = cnv.tl.infercnv(_adata(Yd, var), reference=ref, chunksize=10, inplace=False)
+    _compare_thresholded(got_s.toarray(), want.toarray(), 10, what="ragged csr", max_flips=2)
+    _compare_thresholded(got_d.toarray(), want.toarray(), 10, what="ragged dense", max_flips=2)
