@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Bench of the tl.infercnv hot path (BASELINE.json metric: cells/s through tl.infercnv, 1M x 20k fp32, 1/2/4/8 B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells-total 1000000] [--workloads dense100,dense250,csr100]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--cells-total 1000000] [--workloads dense100,dense250,csr100,graph]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...          # CPU arm: the oracle port on the host cores
 
@@ -13,7 +13,8 @@ One "step" = one full pass of the hot path over this rank's row shard: reference
 when N > 1, mean) -> centre / clip / pyramid smoothing (the dominant kernel) -> exact row median -> per-chunk noise
 threshold -> dense-to-CSR compaction (the reference's ``:455``).  The headline line is window 100 on dense input
 (``dense100``); ``sub`` carries the same measurement for BASELINE configs[2] (``dense250``: window 250) and configs[3]
-(``csr100``: CSR input) on the same cells.
+(``csr100``: CSR input) on the same cells, and ``graph`` = configs[4] (a cells x 1792 CNV matrix -> PCA(50) -> kNN(15) ->
+Leiden, wall-clock per stage).
 
 ``value``   : whole-job cells/s with the input resident in HBM (device-timed, max over ranks).
 ``e2e``     : the same through the public API ``cnv.tl.infercnv(adata)`` with the matrix in pinned HOST memory: H2D of
@@ -60,7 +61,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workloads", default="dense100,dense250,csr100", help="first one is the headline line, the others go to `sub`")
+    ap.add_argument("--workloads", default="dense100,dense250,csr100,graph",
+                    help="first one is the headline line, the others go to `sub` (graph = BASELINE configs[4]: PCA + kNN + Leiden)")
     ap.add_argument("--workload", default=None, help="shorthand for --workloads <one>")
     ap.add_argument("--cells-total", type=int, default=1_000_000, help="cells of the whole job (sharded over the ranks)")
     ap.add_argument("--cells", type=int, default=None, help="cells per GPU (overrides --cells-total: weak scaling)")
@@ -552,7 +554,15 @@ def main():
                    f"every rank runs its {'whole shard' if n_e2e == n_local else f'first {n_e2e} rows of its shard (host memory bound)'}",
         }
 
-    graph_res = measure_graph() if want_graph else None
+    graph_res = None
+    if want_graph:
+        if world > 1:
+            graph_res = measure_graph()  # collectives inside: an exception on one rank must not leave the others waiting
+        else:
+            try:
+                graph_res = measure_graph()
+            except Exception as e:  # single process: the sub-line must not take the headline measurement down with it
+                graph_res = {"error": repr(e)[:400]}
     sampler.stop()
     clocks = None
     if rank == 0:
