@@ -235,6 +235,8 @@ def _to_host(t, out_dtype=None, slab_bytes: int = 32 << 20):
 def _copy_threads() -> int:
     """Host copy threads of this rank: at most 16, and no more than its share of the cores when several ranks (LOCAL_WORLD_SIZE
     / WORLD_SIZE of torchrun) run on the box (first-touching the result arrays is page-fault bound, ~2-4 GB/s per thread)."""
+    if os.environ.get("ICNV_COPY_THREADS"):  # developer override
+        return max(1, int(os.environ["ICNV_COPY_THREADS"]))
     ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
     return max(1, min(16, (os.cpu_count() or 8) // max(1, ranks)))
 
