@@ -40,6 +40,10 @@ constexpr int KNN_BLOCK_BYTES = 2 * KNN_HALF_BYTES;         // 64 KB per tile
 constexpr int KNN_KK = 24;              // candidates kept per query before the exact re-rank (k <= 16 -> 8 of slack)
 constexpr int KNN_STAGES = 2;
 constexpr int KNN_THREADS = 192;
+constexpr int KNN_STATE_WORDS = 2 * KNN_KK * KNN_TILE + KNN_TILE;  // per query tile: keys, ids, meta (32-bit words)
+// candidate tiles per launch: 1024 x 64 KB = 64 MB stays in the 126 MB L2 while every query tile streams it (one launch
+// over 1M points re-read 950 GB from HBM at a 65 % L2 hit rate: ncu, profiles/ncu_knn_1m_r2.csv)
+constexpr int64_t KNN_SUPER_TILES = 1024;
 
 // ------------------------------------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(256) knn_pack_kernel(const float* __restrict__ P, int64_t n, int d, int64_t ld, int64_t n_pad,
@@ -157,7 +161,11 @@ struct __align__(16) KnnSmem {
 // ------------------------------------------------------------------------------------------------ main kernel
 __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __restrict__ packed, const float* __restrict__ packed_q,
                                                                  const float* __restrict__ norms, int64_t n_cand_tiles, int n_ksteps,
-                                                                 int32_t* __restrict__ cand_idx /* [n_q_tiles*128, KK] */) {
+                                                                 int32_t* __restrict__ cand_idx /* [n_q_tiles*128, KK] */,
+                                                                 int64_t t_off, float* __restrict__ state, int resume) {
+    // Candidates are streamed in L2-sized super-blocks (knn_launch): `packed` / `norms` point at candidate tile t_off, this
+    // launch covers n_cand_tiles of them, and a query tile's candidate lists travel between launches through `state`
+    // ([q_tile][keys KK*128 | ids KK*128 | meta 128]; resume != 0: start from it).
     extern __shared__ __align__(1024) unsigned char smem[];
     // layout: [A hi|lo 64 KB][B stage 0 64 KB][B stage 1 64 KB][lists key KK*128*4][lists idx KK*128*4][norms 4 x 128][meta 128][KnnSmem]
     unsigned char* sA = smem;
@@ -248,8 +256,21 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __
         const int quarter = warp & 3;             // the TMEM lanes this warp may touch: 32 * (warp % 4) ..
         const int row = quarter * 32 + lane;      // query row inside the tile
         float thr = INFINITY;                     // current worst key of a full list
-        lmeta[row] = 0;
-        for (int i = 0; i < KNN_KK; ++i) lidx[i * KNN_TILE + row] = -1;
+        float* st_key = state ? state + (size_t)q_tile * KNN_STATE_WORDS : nullptr;
+        int32_t* st_idx = reinterpret_cast<int32_t*>(st_key + KNN_KK * KNN_TILE);
+        int32_t* st_meta = st_idx + KNN_KK * KNN_TILE;
+        if (resume) {
+            const int meta = st_meta[row];
+            lmeta[row] = meta;
+            for (int i = 0; i < KNN_KK; ++i) {
+                lkey[i * KNN_TILE + row] = st_key[i * KNN_TILE + row];
+                lidx[i * KNN_TILE + row] = st_idx[i * KNN_TILE + row];
+            }
+            if ((meta & 0xFF) == KNN_KK) thr = lkey[(meta >> 8) * KNN_TILE + row];
+        } else {
+            lmeta[row] = 0;
+            for (int i = 0; i < KNN_KK; ++i) lidx[i * KNN_TILE + row] = -1;
+        }
         for (int64_t t = 0; t < n_cand_tiles; ++t) {
             const int b = (int)(t & 1);
             mbar_wait(&S->tmem_full[b], (uint32_t)(t >> 1) & 1u);
@@ -281,7 +302,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __
                 if (mn[0] < thr) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (key[j] < thr) thr = knn_insert(lkey, lidx, lmeta, row, key[j], (int32_t)(t * KNN_TILE + c0 + j));
+                        if (key[j] < thr) thr = knn_insert(lkey, lidx, lmeta, row, key[j], (int32_t)((t + t_off) * KNN_TILE + c0 + j));
                 }
             }
             tc_fence_before();
@@ -289,6 +310,13 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_mma_kernel(const float* __
         }
         int32_t* dst = cand_idx + ((int64_t)blockIdx.x * KNN_TILE + row) * KNN_KK;
         for (int i = 0; i < KNN_KK; ++i) dst[i] = lidx[i * KNN_TILE + row];
+        if (st_key) {  // hand the lists to the launch that covers the next candidate super-block
+            st_meta[row] = lmeta[row];
+            for (int i = 0; i < KNN_KK; ++i) {
+                st_key[i * KNN_TILE + row] = lkey[i * KNN_TILE + row];
+                st_idx[i * KNN_TILE + row] = lidx[i * KNN_TILE + row];
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -347,7 +375,8 @@ size_t knn_smem_bytes() { return (size_t)(1 + KNN_STAGES) * KNN_BLOCK_BYTES + (s
 size_t knn_workspace_bytes(int64_t n_all, int64_t nq) {
     const int64_t n_tiles = (n_all + KNN_TILE - 1) / KNN_TILE;
     const int64_t q_tiles = (nq + KNN_TILE - 1) / KNN_TILE;
-    return (size_t)(n_tiles + q_tiles) * KNN_BLOCK_BYTES + (size_t)n_tiles * KNN_TILE * 4 + (size_t)q_tiles * KNN_TILE * KNN_KK * 4 + 4096;
+    return (size_t)(n_tiles + q_tiles) * KNN_BLOCK_BYTES + (size_t)n_tiles * KNN_TILE * 4 + (size_t)q_tiles * KNN_TILE * KNN_KK * 4 +
+           (n_tiles > KNN_SUPER_TILES + KNN_SUPER_TILES / 2 ? (size_t)q_tiles * KNN_STATE_WORDS * 4 : 0) + 4096;
 }
 
 int knn_launch(const float* P, int64_t n_all, int d, int64_t ld, int64_t q0, int64_t nq, int k, int out_ld, int32_t* knn_idx, float* knn_d2,
@@ -379,7 +408,18 @@ int knn_launch(const float* P, int64_t n_all, int d, int64_t ld, int64_t q0, int
     }
     const size_t smem = knn_smem_bytes();
     ICNV_CUDA(cudaFuncSetAttribute(knn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_mma_kernel<<<(unsigned)q_tiles, KNN_THREADS, smem, st>>>(packed, packed_q, norms, n_tiles, (d + 7) / 8, cand);
+    if (n_tiles <= KNN_SUPER_TILES + KNN_SUPER_TILES / 2) {
+        knn_mma_kernel<<<(unsigned)q_tiles, KNN_THREADS, smem, st>>>(packed, packed_q, norms, n_tiles, (d + 7) / 8, cand, 0, nullptr, 0);
+    } else {
+        float* state = reinterpret_cast<float*>(reinterpret_cast<char*>(cand) + (size_t)q_tiles * KNN_TILE * KNN_KK * 4);
+        for (int64_t t0 = 0; t0 < n_tiles; t0 += KNN_SUPER_TILES) {
+            int64_t t1 = std::min(n_tiles, t0 + KNN_SUPER_TILES);
+            if (n_tiles - t1 < KNN_SUPER_TILES / 2) t1 = n_tiles;  // no short tail launch
+            knn_mma_kernel<<<(unsigned)q_tiles, KNN_THREADS, smem, st>>>(packed + (size_t)t0 * (KNN_BLOCK_BYTES / 4), packed_q,
+                                                                         norms + t0 * KNN_TILE, t1 - t0, (d + 7) / 8, cand, t0, state, t0 > 0);
+            if (t1 == n_tiles) break;
+        }
+    }
     ICNV_CUDA(cudaGetLastError());
     knn_rerank_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(P, n_all, d, ld, q0, nq, cand, k, out_ld, knn_idx, knn_d2);
     ICNV_CUDA(cudaGetLastError());

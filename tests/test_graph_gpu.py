@@ -97,6 +97,32 @@ def test_knn_tensor_core_path_at_scale_and_sharded():
     assert torch.equal(torch.cat([i0, i1]), idx) and torch.equal(torch.cat([d0, d1]), dist)
 
 
+def test_knn_candidate_super_blocks_carry_the_lists():
+    """Beyond 1536 candidate tiles (196 608 points) the candidates are streamed in L2-sized super-blocks, one launch each,
+    and a query tile's candidate lists travel between the launches: 270 001 points, 1500 queries in the middle, against a
+    float64 brute force."""
+    import torch
+    from infercnvpy_b200.pp._neighbors import knn_device
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    n, d, k, q0, nq = 270001, 50, 15, 133337, 1500
+    P = torch.randn((n, d), generator=g, device="cuda") + 2.5 * torch.randn((40, d), generator=g, device="cuda")[torch.randint(0, 40, (n,), generator=g, device="cuda")]
+    idx, dist = knn_device(P, k, q0=q0, nq=nq)
+    P64 = P.double()
+    want_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    want_d = torch.empty((nq, k), dtype=torch.float64, device="cuda")
+    for a in range(0, nq, 250):
+        D = torch.cdist(P64[q0 + a : q0 + a + 250], P64).pow(2)
+        v, i = torch.sort(D, dim=1, stable=True)
+        want_i[a : a + 250], want_d[a : a + 250] = i[:, :k], v[:, :k]
+    assert bool((idx[:, 0].long() == torch.arange(q0, q0 + nq, device="cuda")).all())
+    np.testing.assert_allclose((dist.double() ** 2).cpu().numpy(), want_d.cpu().numpy(), rtol=2e-5, atol=1e-5)
+    assert (idx.long() == want_i).float().mean().item() > 0.9999
+    # the neighbours come from every super-block, not only from the last launch
+    assert int(idx.min()) < 1024 * 128 < int(idx.max())
+
+
 def test_community_sweep_handles_hubs_exactly():
     """A star-like graph whose hubs have thousands of neighbours (the sweep used to truncate adjacency lists at
     96 edges): quality of the GPU partition vs the CPU Leiden restatement, and no overflow / truncation."""
