@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256) fuzzy_rows_kernel(const float* __restrict
 // Community detection on the symmetric weighted CNV neighbourhood graph (CSR, both directions stored): the Leiden scheme
 // (Traag, Waltman & van Eck 2019 — what leidenalg runs for scanpy's tl.leiden, /root/reference/src/infercnvpy/tl/
 // __init__.py:24-30) with the RB-configuration quality  sum_c [ w_in(c) - gamma * K_c^2 / 2m ]:
-//   1. local moving   nodes move to the neighbouring community with the best gain
+//   1. local moving   nodes move to the neighbouring community with the best gain (a singleton joins another singleton
+//                     only towards the smaller label)
 //   2. refinement     inside every community of step 1 ("bound") the nodes start again as singletons; a singleton that is
 //                     well connected to its bound ( w(v, C - v) >= gamma * k_v * (K_C - k_v) / 2m ) may join a
 //                     neighbouring sub-community OF THE SAME BOUND if that has a positive gain -> sub-communities are
@@ -255,7 +256,10 @@ __device__ __forceinline__ int32_t sweep_decide(const SweepArgs& a, int64_t i, i
     }
     for (int t = 0; t < nc; ++t) {
         const int32_t c = cs[t];
-        if (a.bound != nullptr && a.csize[c] == 1 && c > ci) continue;  // two singletons: only the larger label moves
+        // two singletons: only the larger label moves (refinement: always; local moving: when the node itself is still a
+        // singleton -- without it, pairs of singletons of a fresh level swap or chase each other under the synchronous
+        // update and a 1M-node kNN graph is still moving thousands of nodes after 200 sweeps)
+        if (a.csize[c] == 1 && c > ci && (a.bound != nullptr || a.csize[ci] == 1)) continue;
         const double g = ws[t] - a.gamma * ki * a.ctot[c] / a.two_m;
         if (g > best + 1e-12 || (best_c != ci && fabs(g - best) <= 1e-12 && c < best_c)) {
             best = g;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(256) community_sweep_heavy_kernel(const SweepA
         for (int t = threadIdx.x; t < LV_HASH && allowed; t += 256) {
             const int32_t c = keys[t];
             if (c < 0) continue;
-            if (refine && a.csize[c] == 1 && c > ci) continue;
+            if (a.csize[c] == 1 && c > ci && (refine || a.csize[ci] == 1)) continue;
             const double g = (double)vals[t] / LV_FIX - a.gamma * ki * a.ctot[c] / a.two_m;
             if (g > best + 1e-12 || (best_c != ci && fabs(g - best) <= 1e-12 && c < best_c)) {
                 best = g;
@@ -495,7 +499,7 @@ int graph_community_sweep(const int64_t* indptr, const int32_t* indices, const f
     double* btot = ctot + n;
     int32_t* csize = reinterpret_cast<int32_t*>(btot + n);
     int32_t* heavy = csize + n;
-    int rc = community_totals(comm, kdeg, n, ctot, bound ? csize : nullptr, st);
+    int rc = community_totals(comm, kdeg, n, ctot, csize, st);
     if (rc) return rc;
     if (bound) {
         rc = community_totals(bound, kdeg, n, btot, nullptr, st);
