@@ -38,6 +38,21 @@ def test_pca_matches_truncated_svd(clones):
         assert err < 5e-3, (c, err)
     # all singular values agree
     np.testing.assert_allclose(np.linalg.norm(got.astype(np.float64), axis=0), sv, rtol=2e-4)
+    # against the EXACT float64 SVD of the same matrix (ARPACK is itself approximate): singular values to float32
+    # accuracy, the 20-dimensional score subspace to 1e-5 (largest principal angle), every component up to its spectral gap
+    Xd = X.toarray().astype(np.float64)
+    U, S, Vt = np.linalg.svd(Xd, full_matrices=False)
+    g64 = got.astype(np.float64)
+    np.testing.assert_allclose(np.linalg.norm(g64, axis=0), S[:20], rtol=5e-6)
+    Qg, _ = np.linalg.qr(g64)
+    cosines = np.linalg.svd(Qg.T @ U[:, :20], compute_uv=False)
+    assert 1.0 - cosines.min() < 1e-9, cosines.min()
+    for c in range(20):
+        exact = U[:, c] * S[c]
+        exact = exact * np.sign(Vt[c, np.abs(Vt[c]).argmax()])  # svd_flip convention: largest |loading| positive
+        gap = min(S[c - 1] - S[c] if c else np.inf, S[c] - S[c + 1])
+        err = np.linalg.norm(g64[:, c] - exact) / S[c]
+        assert err < 3e-6 * max(1.0, S[c] / gap), (c, err, S[c] / gap)
     # keys / errors of the reference wrapper (tl/__init__.py:63-73)
     cnv.tl.pca(adata)
     assert adata.obsm["X_cnv_pca"].shape == (3000, 50)
