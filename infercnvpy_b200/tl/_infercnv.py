@@ -201,7 +201,10 @@ def _to_host(t, out_dtype=None, slab_bytes: int = 32 << 20):
     spans = [(a, min(n, a + per)) for a in range(0, n, per)]
     evs = [None, None]
     main = torch.cuda.current_stream(t.device)
-    side = _PINNED.setdefault(("stream", str(t.device)), torch.cuda.Stream(t.device))
+    skey = ("stream", str(t.device))
+    if skey not in _PINNED:  # one copy stream per device, created once
+        _PINNED[skey] = torch.cuda.Stream(t.device)
+    side = _PINNED[skey]
     side.wait_stream(main)
 
     def issue(i):
