@@ -345,3 +345,36 @@ def test_tsne_affinities_match_numpy_restatement():
     want = np.maximum((C + C.T) / 600.0, 1e-12)
     np.fill_diagonal(want, 0.0)
     np.testing.assert_allclose(P, want, rtol=2e-3, atol=1e-9)
+
+
+def test_reference_workflow_sequence_on_183_cells():
+    """/root/reference/tests/test_tools.py:206-218 (test_workflow) call for call, on a stand-in of the size of the
+    reference's bundled oligodendroglioma data set (183 cells): infercnv -> pca -> neighbors -> tsne -> umap -> leiden ->
+    cnv_score, then the group means behind pl.chromosome_heatmap_summary.  The reference asserts nothing there; here every
+    key it would leave behind exists with the reference's shape / dtype and the planted clones are found."""
+    var = cnv.datasets.synthetic_var(4000, seed=3)
+    X, clone = cnv.datasets.synthetic_counts_with_cnv(183, var, seed=11)
+    adata = cnv.AnnData(X, var=var)
+    cnv.tl.infercnv(adata)
+    cnv.tl.pca(adata)
+    cnv.pp.neighbors(adata)
+    cnv.tl.tsne(adata)
+    cnv.tl.umap(adata)
+    cnv.tl.leiden(adata)
+    cnv.tl.cnv_score(adata)
+    n = adata.n_obs
+    assert sp.issparse(adata.obsm["X_cnv"]) and adata.obsm["X_cnv"].dtype == np.float64 and "chr_pos" in adata.uns["cnv"]
+    assert adata.obsm["X_cnv_pca"].shape == (n, 50) and adata.obsm["X_cnv_pca"].dtype == np.float32
+    assert adata.obsp["cnv_neighbors_connectivities"].shape == (n, n) and adata.obsp["cnv_neighbors_distances"].shape == (n, n)
+    assert adata.uns["cnv_neighbors"]["params"]["n_neighbors"] == 15
+    assert adata.obsm["X_cnv_tsne"].shape == (n, 2) and adata.obsm["X_cnv_umap"].shape == (n, 2)
+    assert np.isfinite(adata.obsm["X_cnv_tsne"]).all() and np.isfinite(adata.obsm["X_cnv_umap"]).all()
+    assert str(adata.obs["cnv_leiden"].dtype) == "category" and adata.obs["cnv_score"].dtype == np.float64
+    codes = adata.obs["cnv_leiden"].cat.codes.values
+    purity = sum(np.bincount(clone[codes == c]).max() for c in np.unique(codes)) / n
+    assert purity > 0.9, purity
+    groups, means = cnv.pl.group_means(adata, "cnv_leiden")
+    assert means.shape == (len(groups), adata.obsm["X_cnv"].shape[1])
+    g0 = groups[0]
+    want = np.asarray(adata.obsm["X_cnv"][np.asarray(adata.obs["cnv_leiden"] == g0)].mean(axis=0)).ravel()
+    np.testing.assert_allclose(means[0], want, rtol=1e-12, atol=1e-15)
