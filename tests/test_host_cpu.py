@@ -288,3 +288,23 @@ def test_bench_clock_sampler_stop_without_start():
     s = bench.ClockSampler.__new__(bench.ClockSampler)
     s.nv, s.thread, s.stop_flag, s.samples, s.period, s.max_mhz = object(), None, threading.Event(), [], 0.004, None
     s.stop()
+
+
+def test_device_csr_row_views_rebase_indptr():
+    """io.DeviceCSR.rows: the row slices tl.infercnv asks for are views with indptr rebased to zero (checked on CPU
+    tensors: the class only does tensor slicing)."""
+    import scipy.sparse as sp
+    import torch
+
+    from infercnvpy_b200.io import DeviceCSR
+
+    rng = np.random.default_rng(1)
+    A = sp.random(40, 17, density=0.3, format="csr", dtype=np.float32, random_state=rng)
+    S = DeviceCSR(torch.from_numpy(A.indptr.astype(np.int64)), torch.from_numpy(A.indices.astype(np.int32)), torch.from_numpy(A.data), A.shape)
+    assert S.shape == (40, 17) and S.nnz == A.nnz and S.format == "csr" and S.dtype == np.float32
+    ip, ix, dv = S.rows(0, 40)
+    assert ip.data_ptr() == S.indptr.data_ptr() and ix.data_ptr() == S.indices.data_ptr()  # whole matrix: no copy
+    for r0, r1 in ((0, 7), (7, 33), (33, 40), (5, 5)):
+        ip, ix, dv = S.rows(r0, r1)
+        sub = A[r0:r1]
+        assert ip.tolist() == sub.indptr.tolist() and ix.tolist() == sub.indices.tolist() and np.array_equal(dv.numpy(), sub.data)
