@@ -54,8 +54,11 @@ class AnnData:
     def copy(self):
         import copy
 
+        def dup(v):  # numpy / scipy / pandas: .copy(); torch: .clone(); anything else (device CSR views) is shared
+            return v.copy() if hasattr(v, "copy") else (v.clone() if hasattr(v, "clone") else v)
+
         return AnnData(
-            self.X.copy(),
+            dup(self.X),
             obs=self.obs.copy(),
             var=self.var.copy(),
             layers={k: v.copy() for k, v in self.layers.items()},

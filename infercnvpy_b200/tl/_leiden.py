@@ -161,8 +161,9 @@ def leiden(
     """Cluster the CNV neighbourhood graph by modularity optimisation (GPU).
 
     Same parameters / keys as the reference (``tl/__init__.py:13-30``); ``resolution`` (default 1) may be passed as
-    keyword.  Writes ``adata.obs[key_added]`` (categorical of strings, "0" = largest cluster); with
-    ``inplace=False`` the labels are returned as a ``pandas.Categorical`` instead.
+    keyword.  Writes ``adata.obs[key_added]`` (categorical of strings, "0" = largest cluster) and ``adata.uns[key_added]``;
+    with ``inplace=False`` a COPY of ``adata`` carrying both is returned and ``adata`` is left alone — the reference passes
+    ``copy=not inplace`` to ``scanpy.tl.leiden`` (``tl/__init__.py:28``), which returns the annotated copy.
     """
     import torch
 
@@ -210,8 +211,8 @@ def leiden(
     lab = lab.cpu().numpy()
     cats = [str(i) for i in range(int(order.numel()))]
     result = pd.Categorical([str(i) for i in lab], categories=cats)
-    if inplace:
-        adata.obs[key_added] = result
-        adata.uns[key_added] = {"params": {"resolution": resolution, "random_state": 0, "n_iterations": -1}}
-    else:
-        return result
+    target = adata if inplace else adata.copy()
+    target.obs[key_added] = result
+    target.uns[key_added] = {"params": {"resolution": resolution, "random_state": 0, "n_iterations": -1}}
+    if not inplace:
+        return target

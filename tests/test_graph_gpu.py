@@ -260,14 +260,17 @@ def test_leiden_and_workflow(clones):
         ncomp, _ = connected_components(A[members][:, members], directed=False)
         assert ncomp == 1, f"cluster {c} is split into {ncomp} components"
     # determinism: a second run gives the same labels
-    again = cnv.tl.leiden(adata, inplace=False)
-    assert list(again) == list(lab)
+    # inplace=False: an annotated COPY comes back (scanpy's copy=True, tl/__init__.py:28) and the input is untouched
+    before = adata.obs["cnv_leiden"].copy()
+    copy = cnv.tl.leiden(adata, inplace=False, key_added="again")
+    assert "again" not in adata.obs.columns and "again" not in adata.uns and adata.obs["cnv_leiden"].equals(before)
+    assert list(copy.obs["again"]) == list(lab) and copy.uns["again"]["params"]["resolution"] == 1.0
     # cnv_score on the clusters: the altered clones score higher than the normal one
     cnv.tl.cnv_score(adata)
     score = adata.obs.groupby("clone", observed=True)["cnv_score"].mean()
     assert score["k0"] < score["k1"] and score["k0"] < score["k2"]
-    res = cnv.tl.leiden(adata, inplace=False, resolution=0.5)
-    assert len(res.categories) <= len(lab.cat.categories)
+    res = cnv.tl.leiden(adata, inplace=False, resolution=0.5).obs["cnv_leiden"]
+    assert len(res.cat.categories) <= len(lab.cat.categories)
 
 
 def _knn_purity(emb, labels, k=10):
