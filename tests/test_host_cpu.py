@@ -308,3 +308,26 @@ def test_device_csr_row_views_rebase_indptr():
         ip, ix, dv = S.rows(r0, r1)
         sub = A[r0:r1]
         assert ip.tolist() == sub.indptr.tolist() and ix.tolist() == sub.indices.tolist() and np.array_equal(dv.numpy(), sub.data)
+
+
+def test_umap_curve_parameters_known_values():
+    """tl.umap fits (a, b) of 1 / (1 + a x^(2b)) like umap-learn's find_ab_params; the values umap-learn reports for its own
+    default (min_dist 0.1) and for scanpy's default (min_dist 0.5), spread 1, are well known."""
+    from infercnvpy_b200.tl._embed import find_ab_params
+
+    a, b = find_ab_params(1.0, 0.1)
+    assert abs(a - 1.5769434603113077) < 2e-3 and abs(b - 0.8950608779109733) < 2e-3
+    a, b = find_ab_params(1.0, 0.5)
+    assert abs(a - 0.5830300205483709) < 2e-3 and abs(b - 1.334166992455648) < 2e-3
+
+
+def test_embedding_wrappers_reject_unsupported_keywords_before_touching_the_gpu():
+    """Like pca / neighbors / leiden: scanpy keywords that are not implemented raise TypeError instead of being dropped."""
+    X = np.zeros((5, 3), dtype=np.float32)
+    a = cnv.AnnData(X, obsm={"X_cnv_pca": np.zeros((5, 4), dtype=np.float32)}, uns={"cnv_neighbors": {}})
+    with pytest.raises(TypeError, match="n_components"):
+        cnv.tl.umap(a, n_components=3)
+    with pytest.raises(TypeError, match="use_fast_tsne"):
+        cnv.tl.tsne(a, use_fast_tsne=True)
+    with pytest.raises(KeyError, match="pp.neighbors"):
+        cnv.tl.umap(cnv.AnnData(X))
